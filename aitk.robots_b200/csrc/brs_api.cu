@@ -1,0 +1,473 @@
+// brs_api.cu -- C ABI (include/brs.h) over the sm_100a kernels in brs_kernels.cuh.
+//
+// Host side only: configuration checks, descriptor precomputation in float64
+// (with the same libm the float64 reference uses), HBM buffer ownership, launch
+// geometry, host<->device copies.  There is no CPU compute path in here: every
+// entry point that produces results launches brs_step_kernel.
+#include "../../include/brs.h"
+#include "brs_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace brs;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(BRS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+struct brs_engine {
+  brs_config cfg;
+  std::vector<brs_robot_desc> robots;
+  std::vector<brs_range_desc> ranges;
+  std::vector<brs_camera_desc> cameras;
+  std::vector<brs_point_desc> lights, smells;
+  int sm_count = 0;
+  int cam_w = 0, cam_h = 0;
+  int rays_range = 0;  // total range rays per world
+  void* buf[BRS_BUF_COUNT_] = {};
+  size_t stride[BRS_BUF_COUNT_] = {};  // bytes per world
+  void* bound[BRS_BUF_COUNT_] = {};
+  RobotDev* d_robots = nullptr;
+  RangeDev* d_ranges = nullptr;
+  CameraDev* d_cameras = nullptr;
+  PointDev* d_lights = nullptr;
+  PointDev* d_smells = nullptr;
+  double2* d_camcs = nullptr;
+  uint32_t* d_rowsky = nullptr;
+  uint32_t* d_rowgnd = nullptr;
+  int T = 32, TA = 0, TB = 0, SL = 1, grid = 1, smem = 0;
+};
+
+static int pow2floor(int x) {
+  int p = 1;
+  while (p * 2 <= x) p *= 2;
+  return p;
+}
+
+extern "C" int brs_abi_version(void) { return BRS_ABI_VERSION; }
+extern "C" const char* brs_last_error(void) { return g_err.c_str(); }
+
+extern "C" int brs_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(BRS_ERR_NO_DEVICE, cudaGetErrorString(e));
+  return n;
+}
+
+template <class T>
+static int to_device(T** dst, const std::vector<T>& src) {
+  const size_t bytes = std::max<size_t>(src.size() * sizeof(T), 16);
+  CK(cudaMalloc((void**)dst, bytes));
+  CK(cudaMemset(*dst, 0, bytes));
+  if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return BRS_OK;
+}
+
+static uint32_t pack_rgb(double r, double g, double b) {
+  return (uint32_t)(int)r | ((uint32_t)(int)g << 8) | ((uint32_t)(int)b << 16) | 0xff000000u;
+}
+
+extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
+  if (!cfg || !out) return fail(BRS_ERR_INVALID, "brs_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != BRS_ABI_VERSION) return fail(BRS_ERR_INVALID, "brs_create: ABI version mismatch");
+  if (cfg->n_worlds < 1) return fail(BRS_ERR_INVALID, "brs_create: n_worlds < 1");
+  if (cfg->n_robots < 1 || cfg->n_robots > BRS_MAX_ROBOTS)
+    return fail(BRS_ERR_INVALID, "brs_create: n_robots out of range 1..BRS_MAX_ROBOTS");
+  if (cfg->seg_cap < 4 || cfg->seg_cap % 4) return fail(BRS_ERR_INVALID, "brs_create: seg_cap must be a positive multiple of 4");
+  if (cfg->n_range < 0 || cfg->n_camera < 0 || cfg->n_light < 0 || cfg->n_smell < 0 || cfg->n_bulbs < 0)
+    return fail(BRS_ERR_INVALID, "brs_create: negative device count");
+  if (!cfg->robots) return fail(BRS_ERR_INVALID, "brs_create: robots == NULL");
+  if ((cfg->n_range && !cfg->ranges) || (cfg->n_camera && !cfg->cameras) || (cfg->n_light && !cfg->lights) ||
+      (cfg->n_smell && !cfg->smells))
+    return fail(BRS_ERR_INVALID, "brs_create: device table missing");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(BRS_ERR_NO_DEVICE, "brs_create: no CUDA device (this engine has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(BRS_ERR_INVALID, "brs_create: bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+
+  brs_engine* e = new brs_engine();
+  e->cfg = *cfg;
+  const int R = cfg->n_robots;
+  e->robots.assign(cfg->robots, cfg->robots + R);
+  if (cfg->n_range) e->ranges.assign(cfg->ranges, cfg->ranges + cfg->n_range);
+  if (cfg->n_camera) e->cameras.assign(cfg->cameras, cfg->cameras + cfg->n_camera);
+  if (cfg->n_light) e->lights.assign(cfg->lights, cfg->lights + cfg->n_light);
+  if (cfg->n_smell) e->smells.assign(cfg->smells, cfg->smells + cfg->n_smell);
+  e->cfg.robots = e->robots.data();
+  e->cfg.ranges = e->ranges.data();
+  e->cfg.cameras = e->cameras.data();
+  e->cfg.lights = e->lights.data();
+  e->cfg.smells = e->smells.data();
+  auto bad = [&](const char* m) {
+    delete e;
+    return fail(BRS_ERR_INVALID, m);
+  };
+  for (auto& d : e->ranges)
+    if (d.robot < 0 || d.robot >= R || !(d.max > 0)) return bad("brs_create: bad range sensor descriptor");
+  for (auto& d : e->lights)
+    if (d.robot < 0 || d.robot >= R) return bad("brs_create: bad light sensor descriptor");
+  for (auto& d : e->smells)
+    if (d.robot < 0 || d.robot >= R) return bad("brs_create: bad smell sensor descriptor");
+  for (auto& d : e->cameras) {
+    if (d.robot < 0 || d.robot >= R || d.width < 4 || d.width % 4 || d.height < 1)
+      return bad("brs_create: bad camera descriptor (width must be a multiple of 4)");
+    if (e->cam_w == 0) {
+      e->cam_w = d.width;
+      e->cam_h = d.height;
+    } else if (e->cam_w != d.width || e->cam_h != d.height)
+      return bad("brs_create: all cameras of an engine must share one image size");
+  }
+  if (cfg->n_light && !cfg->n_bulbs) { /* lights without bulbs read 0: allowed */ }
+
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  e->sm_count = prop.multiProcessorCount;
+
+  // ---- device descriptors, float64, same libm as the float64 reference -------
+  std::vector<RobotDev> rdev(R);
+  for (int r = 0; r < R; ++r) {
+    const brs_robot_desc& d = e->robots[r];
+    const double cx[4] = {d.bbox[0], d.bbox[0], d.bbox[1], d.bbox[1]};
+    const double cy[4] = {d.bbox[3], d.bbox[2], d.bbox[2], d.bbox[3]};
+    for (int k = 0; k < 4; ++k) {
+      rdev[r].corner_dist[k] = std::sqrt((0 - cx[k]) * (0 - cx[k]) + (0 - cy[k]) * (0 - cy[k]));
+      rdev[r].corner_ang[k] = std::atan2(-cx[k], cy[k]);
+    }
+    rdev[r].height = d.height;
+    rdev[r].vx_ramp = d.vx_ramp;
+    rdev[r].vy_ramp = d.vy_ramp;
+    rdev[r].va_ramp = d.va_ramp;
+    rdev[r].rgba = (uint32_t)d.rgba[0] | ((uint32_t)d.rgba[1] << 8) | ((uint32_t)d.rgba[2] << 16) | ((uint32_t)d.rgba[3] << 24);
+  }
+  const double PI2 = 1.5707963267948966;
+  std::vector<RangeDev> gdev(cfg->n_range);
+  e->rays_range = 0;
+  for (int i = 0; i < cfg->n_range; ++i) {
+    const brs_range_desc& d = e->ranges[i];
+    RangeDev& g = gdev[i];
+    memset(&g, 0, sizeof(g));
+    g.robot = d.robot;
+    g.mx = d.dist_from_center * std::cos(d.dir_from_center + PI2);
+    g.my = d.dist_from_center * std::sin(d.dir_from_center + PI2);
+    g.max = d.max;
+    int n = 0;
+    if (d.width != 0) {
+      // inclusive float range -w/2, 0, +w/2 of the reference's fan
+      double cur = -d.width / 2;
+      while (cur <= d.width / 2 && n < 3) {
+        g.cr[n] = std::cos(d.a - cur);
+        g.sr[n] = std::sin(d.a - cur);
+        ++n;
+        cur += d.width / 2;
+      }
+    } else {
+      g.cr[0] = std::cos(d.a);
+      g.sr[0] = std::sin(d.a);
+      n = 1;
+    }
+    g.n_rays = n;
+    e->ranges[i].n_rays = n;
+    e->rays_range += n;
+  }
+  std::vector<CameraDev> cdev(cfg->n_camera);
+  std::vector<double2> camcs((size_t)cfg->n_camera * e->cam_w);
+  for (int i = 0; i < cfg->n_camera; ++i) {
+    const brs_camera_desc& d = e->cameras[i];
+    CameraDev& c = cdev[i];
+    memset(&c, 0, sizeof(c));
+    c.robot = d.robot;
+    c.width = d.width;
+    c.height = d.height;
+    c.mx = d.dist_from_center * std::cos(d.dir_from_center + PI2);
+    c.my = d.dist_from_center * std::sin(d.dir_from_center + PI2);
+    c.max_range = d.max_range;
+    c.color_fade = d.color_fade;
+    c.size_fade = d.size_fade;
+    for (int k = 0; k < d.width; ++k) {
+      const double ang = (double)k / (double)d.width * d.fov - d.fov / 2;
+      camcs[(size_t)i * e->cam_w + k] = make_double2(std::cos(ang), std::sin(ang));
+    }
+  }
+  auto points = [&](const std::vector<brs_point_desc>& src) {
+    std::vector<PointDev> v(src.size());
+    for (size_t i = 0; i < src.size(); ++i) {
+      v[i].robot = src[i].robot;
+      v[i]._pad = 0;
+      v[i].mx = src[i].dist_from_center * std::cos(src[i].dir_from_center + PI2);
+      v[i].my = src[i].dist_from_center * std::sin(src[i].dir_from_center + PI2);
+    }
+    return v;
+  };
+  std::vector<PointDev> ldev = points(e->lights), sdev = points(e->smells);
+  std::vector<uint32_t> rowsky(std::max(e->cam_h, 1)), rowgnd(std::max(e->cam_h, 1));
+  for (int j = 0; j < e->cam_h; ++j) {
+    const double horizon = e->cam_h / 2.0;
+    const double dist = std::fmax(std::fmin(std::fabs(j - horizon) / horizon, 1.0), 0.0);
+    rowsky[j] = pack_rgb(cfg->sky_rgb[0] + cfg->sky_grad[0] * dist, cfg->sky_rgb[1] + cfg->sky_grad[1] * dist,
+                         cfg->sky_rgb[2] + cfg->sky_grad[2] * dist);
+    rowgnd[j] = pack_rgb(cfg->ground_rgb[0] + cfg->ground_grad[0] * dist, cfg->ground_rgb[1] + cfg->ground_grad[1] * dist,
+                         cfg->ground_rgb[2] + cfg->ground_grad[2] * dist);
+  }
+  int rc;
+  if ((rc = to_device(&e->d_robots, rdev)) || (rc = to_device(&e->d_ranges, gdev)) ||
+      (rc = to_device(&e->d_cameras, cdev)) || (rc = to_device(&e->d_lights, ldev)) ||
+      (rc = to_device(&e->d_smells, sdev)) || (rc = to_device(&e->d_camcs, camcs)) ||
+      (rc = to_device(&e->d_rowsky, rowsky)) || (rc = to_device(&e->d_rowgnd, rowgnd))) {
+    brs_destroy(e);
+    return rc;
+  }
+
+  // ---- HBM buffers ----------------------------------------------------------
+  size_t* st = e->stride;
+  st[BRS_BUF_SEG] = (size_t)5 * cfg->seg_cap * 4;
+  st[BRS_BUF_SEG_COUNT] = 4;
+  st[BRS_BUF_WORLD_SIZE] = 8;
+  st[BRS_BUF_BULBS] = (size_t)cfg->n_bulbs * 16;
+  st[BRS_BUF_GRID] = (size_t)cfg->grid_w * cfg->grid_h * 4;
+  st[BRS_BUF_POSE] = st[BRS_BUF_VEL] = st[BRS_BUF_TARGET_VEL] = (size_t)R * 24;
+  st[BRS_BUF_STALLED] = (size_t)R;
+  st[BRS_BUF_RANGE] = (size_t)cfg->n_range * 4;
+  st[BRS_BUF_CAMERA] = (size_t)cfg->n_camera * e->cam_w * e->cam_h * 4;
+  st[BRS_BUF_LIGHT] = (size_t)cfg->n_light * 4;
+  st[BRS_BUF_SMELL] = (size_t)cfg->n_smell * 4;
+  for (int b = 0; b < BRS_BUF_COUNT_; ++b) {
+    const size_t bytes = std::max<size_t>(st[b] * (size_t)cfg->n_worlds, 16);
+    cudaError_t ce = cudaMalloc(&e->buf[b], bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(e->buf[b], 0, bytes);
+    if (ce != cudaSuccess) {
+      brs_destroy(e);
+      return fail(BRS_ERR_CUDA, std::string("brs_create: HBM allocation failed: ") + cudaGetErrorString(ce));
+    }
+  }
+
+  // ---- launch geometry -------------------------------------------------------
+  const int ncols = cfg->n_camera * e->cam_w;
+  const int nother = cfg->n_range + cfg->n_light + cfg->n_smell;
+  e->TA = ncols ? std::min((ncols + 31) / 32 * 32, 256) : 0;
+  if (nother == 0)
+    e->TB = 0;
+  else if (e->TA)
+    e->TB = nother > 8 ? 64 : 32;
+  else
+    e->TB = std::min(std::max((nother + 31) / 32 * 32, 32), 256);
+  // small worlds with few rays: still give the motion phase a full warp
+  e->T = std::max(e->TA + e->TB, 32);
+  if (e->TB == 0 && e->TA == 0) e->TB = 0;
+  e->SL = nother ? std::min(32, pow2floor(std::max(e->TB / nother, 1))) : 1;
+  const SmemLayout L = make_layout(cfg->seg_cap, R, cfg->n_camera, e->cam_w, e->cam_h);
+  e->smem = L.total;
+  if ((size_t)e->smem > prop.sharedMemPerBlockOptin) {
+    brs_destroy(e);
+    return fail(BRS_ERR_UNSUPPORTED, "brs_create: world too large for one CTA's shared memory (seg_cap / camera width)");
+  }
+  cudaError_t ce = cudaFuncSetAttribute(brs_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem);
+  int nb = 0;
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, brs_step_kernel, e->T, e->smem);
+  if (ce != cudaSuccess || nb < 1) {
+    brs_destroy(e);
+    return fail(BRS_ERR_CUDA, std::string("brs_create: kernel does not fit: ") + cudaGetErrorString(ce));
+  }
+  e->grid = std::min(cfg->n_worlds, nb * e->sm_count);
+  *out = e;
+  return BRS_OK;
+}
+
+extern "C" int brs_destroy(brs_engine* e) {
+  if (!e) return BRS_OK;
+  cudaSetDevice(e->cfg.device);
+  for (int b = 0; b < BRS_BUF_COUNT_; ++b)
+    if (e->buf[b]) cudaFree(e->buf[b]);
+  cudaFree(e->d_robots);
+  cudaFree(e->d_ranges);
+  cudaFree(e->d_cameras);
+  cudaFree(e->d_lights);
+  cudaFree(e->d_smells);
+  cudaFree(e->d_camcs);
+  cudaFree(e->d_rowsky);
+  cudaFree(e->d_rowgnd);
+  delete e;
+  return BRS_OK;
+}
+
+static void* cur(brs_engine* e, int which) { return e->bound[which] ? e->bound[which] : e->buf[which]; }
+
+extern "C" int brs_device_ptr(brs_engine* e, int which, void** ptr, size_t* bytes) {
+  if (!e || which < 0 || which >= BRS_BUF_COUNT_) return fail(BRS_ERR_INVALID, "brs_device_ptr: bad argument");
+  if (ptr) *ptr = cur(e, which);
+  if (bytes) *bytes = e->stride[which] * (size_t)e->cfg.n_worlds;
+  return BRS_OK;
+}
+
+extern "C" int brs_bind_output(brs_engine* e, int which, void* device_ptr) {
+  if (!e || which < BRS_BUF_RANGE || which > BRS_BUF_SMELL)
+    return fail(BRS_ERR_INVALID, "brs_bind_output: only observation buffers can be rebound");
+  if (device_ptr && ((uintptr_t)device_ptr & 15)) return fail(BRS_ERR_INVALID, "brs_bind_output: pointer must be 16-byte aligned");
+  e->bound[which] = device_ptr;
+  return BRS_OK;
+}
+
+static int copy_range(brs_engine* e, int which, int first, int n, size_t* off, size_t* bytes) {
+  if (!e || which < 0 || which >= BRS_BUF_COUNT_) return fail(BRS_ERR_INVALID, "copy: bad buffer id");
+  if (n < 0) n = e->cfg.n_worlds - first;
+  if (first < 0 || n < 0 || first + n > e->cfg.n_worlds) return fail(BRS_ERR_INVALID, "copy: world range out of bounds");
+  *off = e->stride[which] * (size_t)first;
+  *bytes = e->stride[which] * (size_t)n;
+  return BRS_OK;
+}
+
+extern "C" int brs_upload(brs_engine* e, int which, const void* host, int first_world, int n_worlds, void* stream) {
+  size_t off, bytes;
+  int rc = copy_range(e, which, first_world, n_worlds, &off, &bytes);
+  if (rc) return rc;
+  if (!host) return fail(BRS_ERR_INVALID, "brs_upload: host == NULL");
+  CK(cudaSetDevice(e->cfg.device));
+  if (bytes) CK(cudaMemcpyAsync((char*)cur(e, which) + off, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return BRS_OK;
+}
+
+extern "C" int brs_download(brs_engine* e, int which, void* host, int first_world, int n_worlds, void* stream) {
+  size_t off, bytes;
+  int rc = copy_range(e, which, first_world, n_worlds, &off, &bytes);
+  if (rc) return rc;
+  if (!host) return fail(BRS_ERR_INVALID, "brs_download: host == NULL");
+  CK(cudaSetDevice(e->cfg.device));
+  if (bytes) CK(cudaMemcpyAsync(host, (const char*)cur(e, which) + off, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return BRS_OK;
+}
+
+extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
+  if (!(flags & BRS_STEP_ALL)) return BRS_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const brs_config& c = e->cfg;
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_worlds = c.n_worlds; p.n_robots = c.n_robots; p.seg_cap = c.seg_cap; p.n_bulbs = c.n_bulbs;
+  p.grid_w = c.grid_w; p.grid_h = c.grid_h;
+  p.n_range = c.n_range; p.n_camera = c.n_camera; p.n_light = c.n_light; p.n_smell = c.n_smell;
+  p.cam_w = e->cam_w; p.cam_h = e->cam_h;
+  p.TA = e->TA; p.TB = e->TB; p.SL = e->SL;
+  p.flags = flags;
+  p.dt = time_step; p.smell_cell = c.smell_cell_size; p.light_mult = c.light_multiplier;
+  p.seg = (const uint32_t*)e->buf[BRS_BUF_SEG];
+  p.seg_count = (const int*)e->buf[BRS_BUF_SEG_COUNT];
+  p.world_size = (const float*)e->buf[BRS_BUF_WORLD_SIZE];
+  p.bulbs = (const float*)e->buf[BRS_BUF_BULBS];
+  p.grid = (const float*)e->buf[BRS_BUF_GRID];
+  p.pose = (double*)e->buf[BRS_BUF_POSE];
+  p.vel = (double*)e->buf[BRS_BUF_VEL];
+  p.tvel = (const double*)e->buf[BRS_BUF_TARGET_VEL];
+  p.stalled = (uint8_t*)e->buf[BRS_BUF_STALLED];
+  p.range_out = (float*)cur(e, BRS_BUF_RANGE);
+  p.cam_out = (uint8_t*)cur(e, BRS_BUF_CAMERA);
+  p.light_out = (float*)cur(e, BRS_BUF_LIGHT);
+  p.smell_out = (float*)cur(e, BRS_BUF_SMELL);
+  p.robots = e->d_robots; p.ranges = e->d_ranges; p.cameras = e->d_cameras;
+  p.lights = e->d_lights; p.smells = e->d_smells;
+  p.cam_cs = e->d_camcs; p.row_sky = e->d_rowsky; p.row_gnd = e->d_rowgnd;
+  brs_step_kernel<<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
+  CK(cudaGetLastError());
+  return BRS_OK;
+}
+
+extern "C" int brs_step_host(brs_engine* e, double time_step, unsigned flags, const double* h_target_vel,
+                             double* h_pose, uint8_t* h_stalled, float* h_range, uint8_t* h_camera, float* h_light,
+                             float* h_smell, void* stream) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_step_host: null engine");
+  int rc;
+  if (h_target_vel && (rc = brs_upload(e, BRS_BUF_TARGET_VEL, h_target_vel, 0, -1, stream))) return rc;
+  if ((rc = brs_step(e, time_step, flags, stream))) return rc;
+  if (h_pose && (rc = brs_download(e, BRS_BUF_POSE, h_pose, 0, -1, stream))) return rc;
+  if (h_stalled && (rc = brs_download(e, BRS_BUF_STALLED, h_stalled, 0, -1, stream))) return rc;
+  if (h_range && (rc = brs_download(e, BRS_BUF_RANGE, h_range, 0, -1, stream))) return rc;
+  if (h_camera && (rc = brs_download(e, BRS_BUF_CAMERA, h_camera, 0, -1, stream))) return rc;
+  if (h_light && (rc = brs_download(e, BRS_BUF_LIGHT, h_light, 0, -1, stream))) return rc;
+  if (h_smell && (rc = brs_download(e, BRS_BUF_SMELL, h_smell, 0, -1, stream))) return rc;
+  return BRS_OK;
+}
+
+extern "C" int brs_synchronize(brs_engine* e, void* stream) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_synchronize: null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return BRS_OK;
+}
+
+extern "C" int brs_count_tests(brs_engine* e, unsigned flags, void* stream, unsigned long long* tests) {
+  if (!e || !tests) return fail(BRS_ERR_INVALID, "brs_count_tests: null argument");
+  const brs_config& c = e->cfg;
+  std::vector<int> cnt(c.n_worlds);
+  CK(cudaSetDevice(c.device));
+  CK(cudaMemcpyAsync(cnt.data(), e->buf[BRS_BUF_SEG_COUNT], (size_t)c.n_worlds * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  const unsigned long long R = c.n_robots;
+  unsigned long long per_seg = 0;  // tests per visible segment
+  if (flags & BRS_STEP_MOVE) per_seg += R * 4;
+  if (flags & BRS_STEP_SENSE) per_seg += (unsigned long long)e->rays_range + (unsigned long long)c.n_light * c.n_bulbs;
+  if (flags & BRS_STEP_CAMERA) per_seg += (unsigned long long)c.n_camera * e->cam_w;
+  unsigned long long total = 0;
+  for (int w = 0; w < c.n_worlds; ++w) {
+    const unsigned long long S = (unsigned long long)std::min(std::max(cnt[w], 0), c.seg_cap);
+    total += per_seg * (S + 4 * (R - 1));
+  }
+  *tests = total;
+  return BRS_OK;
+}
+
+extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem_bytes, int* sm_count) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_launch_info: null engine");
+  if (threads) *threads = e->T;
+  if (ctas) *ctas = e->grid;
+  if (smem_bytes) *smem_bytes = e->smem;
+  if (sm_count) *sm_count = e->sm_count;
+  return BRS_OK;
+}
+
+extern "C" int brs_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz) {
+  if (!tflops) return fail(BRS_ERR_INVALID, "brs_measure_fp32_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRS_ERR_NO_DEVICE, "brs_measure_fp32_peak: no such CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  float* d = nullptr;
+  CK(cudaMalloc(&d, 16));
+  const int threads = 1024, blocks = prop.multiProcessorCount * 2;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  brs_ffma_kernel<<<blocks, threads>>>(d, iters / 4 + 1, 1.0000001f, 1e-7f);  // warm-up
+  CK(cudaEventRecord(a));
+  brs_ffma_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-7f);
+  CK(cudaEventRecord(b));
+  CK(cudaEventSynchronize(b));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  const double flops = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  if (sm_clock_mhz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    *sm_clock_mhz = khz / 1000.0;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  return BRS_OK;
+}

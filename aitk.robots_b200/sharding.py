@@ -1,0 +1,85 @@
+# -*- coding: utf-8 -*-
+"""Multi-GPU data parallelism: worlds are independent, so a batch shards as
+contiguous world ranges, one process per GPU, with no collective on the data
+path.  The only exchange is the optional all-gather of observations into one
+training batch (BASELINE.json north_star); the kernels write straight into
+this rank's slice of the gather buffer (brs_bind_output), so no staging copy
+precedes the collective (NCCL in-place all-gather).
+"""
+
+import torch
+import torch.distributed as dist
+
+
+def partition(n_worlds, world_size, rank):
+    """Contiguous [first, first+count) range of `rank`; remainders go to the low ranks."""
+    base, rem = divmod(int(n_worlds), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+def all_gather_worlds(local, counts=None, group=None):
+    """All-gather per-rank [n_r, ...] tensors along dim 0 (works on gloo and nccl)."""
+    ws = dist.get_world_size(group)
+    if counts is None or len(set(counts)) == 1:
+        out = local.new_empty((local.shape[0] * ws,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # ragged shards: pad to the largest, gather once, trim
+    m = max(counts)
+    padded = local.new_zeros((m,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    out = local.new_empty((m * ws,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * m : r * m + c] for r, c in enumerate(counts)], dim=0)
+
+
+class ShardedWorlds:
+    """This rank's shard of a global batch + the observation all-gather.
+
+    scene_fn(first_world, count) -> SceneBatch must be deterministic in
+    (first_world, count) so that shards compose into the same global batch
+    irrespective of the number of ranks (the generators in scenes.py are, for
+    chunk-aligned shards).
+    """
+
+    def __init__(self, scene_fn, n_worlds, device=None, group=None):
+        from .engine import BatchEngine
+
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_worlds = int(n_worlds)
+        self.counts = [partition(n_worlds, self.world_size, r)[1] for r in range(self.world_size)]
+        self.first, self.count = partition(n_worlds, self.world_size, self.rank)
+        self.device = torch.cuda.current_device() if device is None else device
+        self.engine = BatchEngine(scene_fn(self.first, self.count), device=self.device)
+        self._gather = {}
+
+    def step(self, time_step=None, flags=7, stream=0):
+        self.engine.step(time_step, flags, stream)
+
+    def gather_buffer(self, name):
+        """Allocate the global observation tensor and make the kernels write this
+        rank's slice of it directly (equal shard sizes only)."""
+        if len(set(self.counts)) != 1:
+            raise ValueError("in-place gather needs equal shards; use all_gather()")
+        local = self.engine.tensor(name)
+        full = torch.empty((self.n_worlds,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        mine = full[self.first:self.first + self.count]
+        self.engine.bind_output(name, mine)
+        self._gather[name] = (full, mine)
+        return full
+
+    def all_gather(self, name):
+        """Observation `name` of every world on every rank."""
+        if name in self._gather:
+            full, mine = self._gather[name]
+            if self.world_size > 1:
+                dist.all_gather_into_tensor(full, mine, group=self.group)  # in place: mine is full's slice
+            return full
+        local = self.engine.tensor(name)
+        if self.world_size == 1:
+            return local
+        return all_gather_worlds(local, self.counts, self.group)

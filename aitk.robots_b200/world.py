@@ -1,0 +1,376 @@
+# -*- coding: utf-8 -*-
+"""Drop-in facade: World / Robot / add_device / get_distance / take_picture.
+
+Mirrors the public names of upstream aitk/robots (world.py, robot.py,
+devices/*.py; BASELINE.json north_star lists them) for ONE world; every number
+it returns was computed by the CUDA engine on a batch of one (or, through
+``World.batch``, on a batch of identical copies).  No arithmetic of the hot
+path lives here, and nothing falls back to the CPU: stepping without a CUDA
+device raises.
+"""
+
+import math
+
+import numpy as np
+
+from . import _cabi as cabi
+from .scenes import CameraSpec, LightSpec, RangeSpec, RobotSpec, SceneBatch, SmellSpec, smell_grid
+
+PI_OVER_180 = math.pi / 180.0
+
+COLORS = {
+    "black": (0, 0, 0), "white": (255, 255, 255), "red": (255, 0, 0), "green": (0, 128, 0),
+    "lime": (0, 255, 0), "blue": (0, 0, 255), "yellow": (255, 255, 0), "cyan": (0, 255, 255),
+    "magenta": (255, 0, 255), "orange": (255, 165, 0), "purple": (128, 0, 128), "pink": (255, 192, 203),
+    "grey": (128, 128, 128), "gray": (128, 128, 128), "brown": (165, 42, 42),
+}
+
+
+def to_rgba(color):
+    if isinstance(color, str):
+        r, g, b = COLORS[color.lower()]
+        return (r, g, b, 255)
+    c = tuple(int(v) for v in color)
+    return c if len(c) == 4 else c + (255,)
+
+
+class _Device:
+    _spec_cls = None
+
+    def __init__(self):
+        self.robot = None
+        self._index = None  # index among devices of the same kind in the world
+
+    def _world(self):
+        if self.robot is None or self.robot.world is None:
+            raise RuntimeError("device is not attached to a robot in a world")
+        return self.robot.world
+
+
+class RangeSensor(_Device):
+    def __init__(self, position=(8, 0), a=0, max=20, width=1.0, name="sensor"):
+        super().__init__()
+        self.spec = RangeSpec(position=(float(position[0]), float(position[1])), a=float(a), max=float(max),
+                              width=float(width), name=name)
+        self.name = name
+
+    def get_max(self):
+        return self.spec.max
+
+    def get_distance(self):
+        w = self._world()
+        w._ensure_sensed()
+        return float(w._obs["range"][0, self._index])
+
+    def get_reading(self):
+        return self.get_distance() / self.spec.max
+
+
+class Camera(_Device):
+    def __init__(self, width=64, height=32, a=60, colorsFadeWithDistance=0.9, sizeFadeWithDistance=1.0,
+                 max_range=1000, position=(0, 0), name="camera"):
+        super().__init__()
+        self.spec = CameraSpec(width=int(width), height=int(height), a=float(a),
+                               colorsFadeWithDistance=float(colorsFadeWithDistance),
+                               sizeFadeWithDistance=float(sizeFadeWithDistance), max_range=float(max_range),
+                               position=(float(position[0]), float(position[1])), name=name)
+        self.name = name
+
+    def take_picture(self, as_array=False):
+        """RGBA picture of what the camera sees now (lazy, like upstream)."""
+        w = self._world()
+        img = w._render()[0, self._index]
+        if as_array:
+            return img.copy()
+        from PIL import Image
+
+        return Image.fromarray(img, "RGBA")
+
+    get_image = take_picture
+
+
+class LightSensor(_Device):
+    def __init__(self, position=(0, 0), name="light"):
+        super().__init__()
+        self.spec = LightSpec(position=(float(position[0]), float(position[1])), name=name)
+        self.name = name
+
+    def get_brightness(self):
+        w = self._world()
+        w._ensure_sensed()
+        return float(w._obs["light"][0, self._index])
+
+    get_reading = get_brightness
+
+
+class SmellSensor(_Device):
+    def __init__(self, position=(0, 0), name="smell"):
+        super().__init__()
+        self.spec = SmellSpec(position=(float(position[0]), float(position[1])), name=name)
+        self.name = name
+
+    def get_reading(self):
+        w = self._world()
+        w._ensure_sensed()
+        return float(w._obs["smell"][0, self._index])
+
+
+class Bulb:
+    def __init__(self, color, x, y, z=0.0, brightness=1.0, name="bulb"):
+        self.color, self.x, self.y, self.z, self.brightness, self.name = to_rgba(color), x, y, z, brightness, name
+
+
+class Robot:
+    """Robot(x, y, a) with ``a`` in degrees, as upstream."""
+
+    def __init__(self, x=0, y=0, a=0, color="red", name="Robbie", height=0.25, max_trans_velocity=2.0,
+                 max_rotate_velocity=math.pi / 4, bbox=None):
+        self.world = None
+        self.name = name
+        self._slot = None
+        self._pose = [float(x), float(y), float(a) * PI_OVER_180]
+        self._tvel = [0.0, 0.0, 0.0]
+        self.color = to_rgba(color)
+        self.height = float(height)
+        self.max_trans_velocity = float(max_trans_velocity)
+        self.max_rotate_velocity = float(max_rotate_velocity)
+        self.bbox = tuple(float(v) for v in (bbox if bbox is not None else RobotSpec().bbox))
+        self._devices = []
+        self._pending = True  # constructor / set_pose values not yet uploaded
+
+    # state (read back from the engine after every step)
+    def _state(self, key, k):
+        w = self.world
+        if w is not None and w._engine is not None and not self._pending:
+            return float(w._state[key][0, self._slot, k])
+        return self._pose[k]
+
+    @property
+    def x(self):
+        return self._state("pose", 0)
+
+    @property
+    def y(self):
+        return self._state("pose", 1)
+
+    @property
+    def a(self):
+        return self._state("pose", 2)
+
+    @property
+    def stalled(self):
+        w = self.world
+        if w is not None and w._engine is not None:
+            return bool(w._state["stalled"][0, self._slot])
+        return False
+
+    def get_pose(self):
+        return (self.x, self.y, self.a)
+
+    def set_pose(self, x=None, y=None, a=None):
+        """a in degrees."""
+        cur = list(self.get_pose())
+        if x is not None:
+            cur[0] = float(x)
+        if y is not None:
+            cur[1] = float(y)
+        if a is not None:
+            cur[2] = float(a) * PI_OVER_180
+        self._pose = cur
+        self._pending = True
+        if self.world is not None:
+            self.world._dirty = True
+
+    def add_device(self, device):
+        device.robot = self
+        self._devices.append(device)
+        if self.world is not None:
+            self.world._dirty = True
+        return device
+
+    def __getitem__(self, item):
+        if isinstance(item, int):
+            return self._devices[item]
+        for d in self._devices:
+            if d.name == item:
+                return d
+        raise KeyError(item)
+
+    def move(self, translate, rotate):
+        self._tvel[0] = translate * self.max_trans_velocity
+        self._tvel[2] = rotate * self.max_rotate_velocity
+
+    def forward(self, translate):
+        self._tvel[0] = translate * self.max_trans_velocity
+
+    def backward(self, translate):
+        self._tvel[0] = -translate * self.max_trans_velocity
+
+    def turn(self, rotate):
+        self._tvel[2] = rotate * self.max_rotate_velocity
+
+    def stop(self):
+        self._tvel = [0.0, 0.0, 0.0]
+
+    def _spec(self):
+        return RobotSpec(bbox=self.bbox, height=self.height, rgba=self.color,
+                         max_trans_velocity=self.max_trans_velocity, max_rotate_velocity=self.max_rotate_velocity,
+                         devices=[d.spec for d in self._devices])
+
+
+class World:
+    def __init__(self, width=500, height=250, seed=0, boundary_wall=True, boundary_wall_color="purple",
+                 ground_color="green", smell_cell_size=None, time_step=0.1, device=0):
+        self.width, self.height = float(width), float(height)
+        self.seed = seed
+        self.time = 0.0
+        self.time_step = time_step
+        self.ground_color = to_rgba(ground_color)
+        self.smell_cell_size = smell_cell_size if smell_cell_size else max(width, height) / 20.0
+        self.device = device
+        self._segments = []  # (x1, y1, x2, y2, rgba)
+        self._bulbs = []
+        self._food = []
+        self._robots = []
+        self._engine = None
+        self._dirty = True
+        self._sensed = False
+        self._state = {}
+        self._obs = {}
+        if boundary_wall:
+            c = to_rgba(boundary_wall_color)
+            w, h = self.width, self.height
+            for s in ((0, 0, w, 0), (0, 0, 0, h), (0, h, w, h), (w, 0, w, h)):
+                self._segments.append(s + (c,))
+
+    # -- construction ------------------------------------------------------------
+    def add_wall(self, color, x1, y1, x2, y2, box=True):
+        c = to_rgba(color)
+        if box:
+            pts = [(x1, y1), (x2, y1), (x2, y2), (x1, y2)]
+            for k in range(4):
+                a, b = pts[k], pts[(k + 1) % 4]
+                self._segments.append((a[0], a[1], b[0], b[1], c))
+        else:
+            self._segments.append((x1, y1, x2, y2, c))
+        self._dirty = True
+
+    def add_bulb(self, color, x, y, z=0.0, brightness=1.0, name="bulb"):
+        b = Bulb(color, x, y, z, brightness, name)
+        self._bulbs.append(b)
+        self._dirty = True
+        return b
+
+    def add_food(self, x, y, standard_deviation):
+        self._food.append((x, y, standard_deviation))
+        self._dirty = True
+
+    def add_robot(self, robot):
+        if len(self._robots) >= cabi.BRS_MAX_ROBOTS:
+            raise ValueError("at most %d robots per world" % cabi.BRS_MAX_ROBOTS)
+        robot.world = self
+        robot._slot = len(self._robots)
+        self._robots.append(robot)
+        self._dirty = True
+        return robot
+
+    # -- batch form --------------------------------------------------------------
+    def to_scene(self, copies=1):
+        """This world as a SceneBatch of `copies` identical worlds."""
+        if not self._robots:
+            raise RuntimeError("world has no robots")
+        n = len(self._segments)
+        cap = max((n + 3) // 4 * 4, 4)
+        seg = np.zeros((1, 4, cap), dtype=np.float32)
+        rgba = np.zeros((1, cap, 4), dtype=np.uint8)
+        for j, (x1, y1, x2, y2, c) in enumerate(self._segments):
+            seg[0, :, j] = (x1, y1, x2, y2)
+            rgba[0, j] = c
+        pose = np.array([[r.get_pose() for r in self._robots]], dtype=np.float64)
+        tvel = np.array([[r._tvel for r in self._robots]], dtype=np.float64)
+        bulbs = None
+        if self._bulbs:
+            bulbs = np.array([[(b.x, b.y, b.z, b.brightness) for b in self._bulbs]], dtype=np.float32)
+        ws = np.array([[self.width, self.height]], dtype=np.float32)
+        food, grid = None, None
+        if self._food:
+            food = np.array([self._food], dtype=np.float32)
+            grid = smell_grid(ws, food, self.smell_cell_size)
+        rep = lambda a: None if a is None else np.repeat(a, copies, axis=0)  # noqa: E731
+        return SceneBatch(world_size=rep(ws), seg=rep(seg), seg_rgba=rep(rgba),
+                          seg_count=np.full(copies, n, dtype=np.int32), pose=rep(pose), target_vel=rep(tvel),
+                          robots=[r._spec() for r in self._robots], bulbs=rep(bulbs), grid=rep(grid),
+                          smell_cell_size=self.smell_cell_size if self._food else 0.0, food=rep(food),
+                          time_step=self.time_step, name="world")
+
+    def batch(self, copies, device=None):
+        """BatchEngine stepping `copies` replicas of this world on the GPU."""
+        from .engine import BatchEngine
+
+        return BatchEngine(self.to_scene(copies), device=self.device if device is None else device)
+
+    # -- engine plumbing -----------------------------------------------------------
+    def _build(self):
+        from .engine import BatchEngine
+
+        if self._engine is not None:
+            self._engine.close()
+        idx = {RangeSensor: 0, Camera: 0, LightSensor: 0, SmellSensor: 0}
+        for r in self._robots:
+            for d in r._devices:
+                d._index = idx[type(d)]
+                idx[type(d)] += 1
+        self._engine = BatchEngine(self.to_scene(1), device=self.device)
+        for r in self._robots:
+            r._pending = False
+        self._dirty = False
+        self._sensed = False
+        self._pull_state()
+
+    def _pull_state(self):
+        e = self._engine
+        self._state = {"pose": e.download("pose"), "stalled": e.download("stalled")}
+
+    def _pull_obs(self):
+        e = self._engine
+        self._obs = {k: e.download(k) for k in ("range", "light", "smell")}
+        self._sensed = True
+
+    def _ensure_engine(self):
+        if self._dirty or self._engine is None:
+            self._build()
+
+    def _ensure_sensed(self):
+        self._ensure_engine()
+        if not self._sensed:
+            self.update()
+
+    def _render(self):
+        self._ensure_engine()
+        self._engine.step(self.time_step, cabi.STEP_CAMERA)
+        return self._engine.download("camera")
+
+    # -- stepping --------------------------------------------------------------------
+    def step(self, time_step=None):
+        """One tick: move every robot, refresh every device, advance the clock."""
+        self._ensure_engine()
+        dt = self.time_step if time_step is None else time_step
+        self._engine.upload("target_vel", np.array([[r._tvel for r in self._robots]], dtype=np.float64))
+        self._engine.step(dt, cabi.STEP_MOVE | cabi.STEP_SENSE)
+        self.time = round(self.time + dt, 10)
+        self._pull_state()
+        self._pull_obs()
+
+    def update(self):
+        """Refresh the devices without moving (upstream World.update)."""
+        self._ensure_engine()
+        self._engine.step(self.time_step, cabi.STEP_SENSE)
+        self._pull_obs()
+
+    def steps(self, n, time_step=None):
+        for _ in range(int(n)):
+            self.step(time_step)
+
+    def seconds(self, seconds, time_step=None):
+        dt = self.time_step if time_step is None else time_step
+        self.steps(round(seconds / dt), time_step)

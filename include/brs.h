@@ -1,0 +1,191 @@
+/*
+ * brs.h -- C ABI of the batched robot stepping engine (libbrs.so).
+ *
+ * This is the drop-in boundary for the aitk.robots `World.step` hot path
+ * (BASELINE.json north_star).  The reference exposes no
+ * FFI / plugin interface at all -- /root/reference/setup.py:21-44 ships no
+ * code and delegates to the un-vendored `aitk` distribution (setup.py:29) -- so
+ * each entry point below names the upstream *Python* call it stands in for.
+ * Upstream file names are from SURVEY.md section 1 (aitk/robots/...); line numbers
+ * cannot be cited because the source is not mounted.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, scalars.  No torch / C++ types.
+ *   - every function returns 0 on success or a negative brs_status; the text of
+ *     the last failure on the calling thread is brs_last_error().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All
+ *     work is enqueued asynchronously; the caller synchronises.
+ *   - the engine owns its device buffers (HBM).  brs_device_ptr() exposes them
+ *     so Python can wrap them zero-copy (torch via __cuda_array_interface__);
+ *     brs_bind_output() redirects an observation buffer to caller memory, e.g.
+ *     a slice of an NCCL all-gather buffer.
+ *   - there is no CPU fallback: without a CUDA device brs_create() fails.
+ *
+ * Angles are radians, lengths are world units (cm upstream), y grows downward.
+ */
+#ifndef BRS_H
+#define BRS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRS_ABI_VERSION 1
+#define BRS_MAX_ROBOTS 8 /* robots per world */
+
+typedef enum brs_status {
+  BRS_OK = 0,
+  BRS_ERR_INVALID = -1, /* bad argument / configuration */
+  BRS_ERR_CUDA = -2,    /* CUDA runtime error, see brs_last_error() */
+  BRS_ERR_NO_DEVICE = -3,
+  BRS_ERR_UNSUPPORTED = -4
+} brs_status;
+
+/* Robot slot r of every world (upstream robot.py: Robot.__init__, bounding box). */
+typedef struct brs_robot_desc {
+  double bbox[4]; /* min_x, max_x, min_y, max_y in the robot frame */
+  double height;  /* 0..1, camera strip height of this robot (Hit.height) */
+  double vx_ramp, vy_ramp, va_ramp; /* max velocity change per second */
+  uint8_t rgba[4]; /* colour seen by other robots' cameras */
+  int32_t _pad;
+} brs_robot_desc;
+
+/* upstream devices/rangesensors.py: RangeSensor(position, a, max, width) */
+typedef struct brs_range_desc {
+  int32_t robot;  /* robot slot */
+  int32_t n_rays; /* 1 (width == 0) or 3 (-w/2, 0, +w/2) */
+  double dist_from_center, dir_from_center; /* mount point, polar, robot frame */
+  double a;     /* heading offset, radians */
+  double max;   /* maximum range */
+  double width; /* beam width, radians */
+} brs_range_desc;
+
+/* upstream devices/cameras.py: Camera(width, height, a, ...) */
+typedef struct brs_camera_desc {
+  int32_t robot;
+  int32_t width, height; /* image size; width % 4 == 0 */
+  int32_t _pad;
+  double dist_from_center, dir_from_center;
+  double fov; /* radians */
+  double max_range;
+  double color_fade, size_fade; /* colorsFadeWithDistance, sizeFadeWithDistance */
+} brs_camera_desc;
+
+/* upstream devices/lightsensors.py / smellsensors.py: mount point only */
+typedef struct brs_point_desc {
+  int32_t robot;
+  int32_t _pad;
+  double dist_from_center, dir_from_center;
+} brs_point_desc;
+
+typedef struct brs_config {
+  int32_t abi_version; /* BRS_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t n_worlds;    /* worlds in this engine (this rank's shard) */
+  int32_t n_robots;    /* robots per world, 1..BRS_MAX_ROBOTS */
+  int32_t seg_cap;     /* wall-segment capacity per world, multiple of 4 */
+  int32_t n_bulbs;     /* bulbs per world (0 = none) */
+  int32_t grid_w, grid_h; /* smell grid cells (0 = no grid) */
+  int32_t n_range, n_camera, n_light, n_smell; /* devices per world */
+  double smell_cell_size;
+  double light_multiplier;
+  /* camera sky / ground colour = base + grad * |j - H/2| / (H/2) */
+  double sky_rgb[3], sky_grad[3], ground_rgb[3], ground_grad[3];
+  const brs_robot_desc* robots;   /* [n_robots] */
+  const brs_range_desc* ranges;   /* [n_range] */
+  const brs_camera_desc* cameras; /* [n_camera], all the same width x height */
+  const brs_point_desc* lights;   /* [n_light] */
+  const brs_point_desc* smells;   /* [n_smell] */
+} brs_config;
+
+/* Device buffers, all leading dimension = world.                      dtype, shape        */
+typedef enum brs_buffer {
+  BRS_BUF_SEG = 0,      /* wall store, SoA rows x1|y1|x2|y2|rgba       u32/f32 [B][5][seg_cap]  */
+  BRS_BUF_SEG_COUNT,    /* used segments per world                     i32 [B]                  */
+  BRS_BUF_WORLD_SIZE,   /* width, height                               f32 [B][2]               */
+  BRS_BUF_BULBS,        /* x, y, z, brightness                         f32 [B][n_bulbs][4]      */
+  BRS_BUF_GRID,         /* smell field                                 f32 [B][grid_h][grid_w]  */
+  BRS_BUF_POSE,         /* x, y, a                                     f64 [B][R][3]            */
+  BRS_BUF_VEL,          /* actual vx, vy, va                           f64 [B][R][3]            */
+  BRS_BUF_TARGET_VEL,   /* target vx, vy, va (Robot.move)              f64 [B][R][3]            */
+  BRS_BUF_STALLED,      /* collision flag of the last step             u8  [B][R]               */
+  BRS_BUF_RANGE,        /* RangeSensor.get_distance()                  f32 [B][n_range]         */
+  BRS_BUF_CAMERA,       /* Camera.take_picture(), RGBA                 u8  [B][n_camera][H][W][4] */
+  BRS_BUF_LIGHT,        /* LightSensor value                           f32 [B][n_light]         */
+  BRS_BUF_SMELL,        /* SmellSensor value                           f32 [B][n_smell]         */
+  BRS_BUF_COUNT_
+} brs_buffer;
+
+/* brs_step flags */
+#define BRS_STEP_MOVE 1u    /* Robot.step for every robot (motion + collision) */
+#define BRS_STEP_SENSE 2u   /* RangeSensor / LightSensor / SmellSensor update  */
+#define BRS_STEP_CAMERA 4u  /* Camera rays + take_picture into BRS_BUF_CAMERA  */
+#define BRS_STEP_ALL 7u
+
+typedef struct brs_engine brs_engine;
+
+int brs_abi_version(void);
+const char* brs_last_error(void);
+
+/* Number of CUDA devices visible, or a negative status. */
+int brs_device_count(void);
+
+/* World(...) + add_robot/add_device for every world of the batch
+ * (upstream world.py: World.__init__, add_robot; robot.py: add_device). */
+int brs_create(const brs_config* cfg, brs_engine** out);
+int brs_destroy(brs_engine* e);
+
+/* Device pointer / byte size of an engine buffer (zero-copy hand-off). */
+int brs_device_ptr(brs_engine* e, int which, void** ptr, size_t* bytes);
+
+/* Redirect an observation buffer (BRS_BUF_RANGE..BRS_BUF_SMELL) to caller-owned
+ * device memory of at least the engine's size for it.  ptr == NULL restores
+ * the engine's own buffer. */
+int brs_bind_output(brs_engine* e, int which, void* device_ptr);
+
+/* Host <-> device copies of a whole buffer or of worlds [first, first+count).
+ * `host` may be pageable or pinned; copies are asynchronous on `stream` when
+ * pinned.  (upstream: World.add_wall / add_bulb / Robot.set_pose / Robot.move
+ * write these fields; Robot.get_pose / device getters read them.) */
+int brs_upload(brs_engine* e, int which, const void* host, int first_world, int n_worlds, void* stream);
+int brs_download(brs_engine* e, int which, void* host, int first_world, int n_worlds, void* stream);
+
+/* World.step(time_step) over every world of the engine: one fused kernel
+ * launch (upstream world.py: World.step -> robot.py: Robot.step, Robot.update
+ * -> devices/*.update; cameras.py: Camera.take_picture when BRS_STEP_CAMERA). */
+int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
+
+/* Same step driven with HOST buffers (the end-to-end path): copies target
+ * velocities host->device, steps, and copies every non-NULL observation back
+ * device->host, all on `stream`.  h_* should be pinned. */
+int brs_step_host(brs_engine* e, double time_step, unsigned flags,
+                  const double* h_target_vel, /* [B][R][3] or NULL */
+                  double* h_pose,             /* [B][R][3] or NULL */
+                  uint8_t* h_stalled,         /* [B][R] or NULL */
+                  float* h_range, uint8_t* h_camera, float* h_light, float* h_smell,
+                  void* stream);
+
+/* Block the calling host thread until `stream` has drained. */
+int brs_synchronize(brs_engine* e, void* stream);
+
+/* Ray-segment tests one brs_step(flags) performs per call over the whole
+ * engine, counted algorithmically: needs the segment counts,
+ * so it reads BRS_BUF_SEG_COUNT back (synchronises `stream`). */
+int brs_count_tests(brs_engine* e, unsigned flags, void* stream, unsigned long long* tests);
+
+/* Launch geometry chosen for this engine (for reports): threads per CTA,
+ * CTAs in the persistent grid, dynamic shared memory bytes. */
+int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem_bytes, int* sm_count);
+
+/* FP32 FFMA throughput microbenchmark on the engine's device: runs `iters`
+ * dependent-chain FFMA sweeps on every SM and returns TFLOP/s (2 flop / FFMA)
+ * timed with CUDA events.  Used only for the roofline denominator. */
+int brs_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRS_H */

@@ -1,0 +1,177 @@
+# -*- coding: utf-8 -*-
+"""Known-answer tests of the CPU restatement oracle (hand-derivable results,
+SURVEY.md section 4 item 1) and its golden fixtures.  CPU only."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import aitk_oracle as orc
+from oracle import scene_adapter as sa
+import aitk_robots_b200 as rb
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_intersect_axis_aligned():
+    # ray along +x from (0,5) of length 100 against the vertical wall x=40
+    assert orc.intersect_hit(0, 5, 100, 5, 40, 0, 40, 10) == (40.0, 5.0)
+    # parallel: no hit
+    assert orc.intersect_hit(0, 5, 100, 5, 0, 7, 100, 7) is None
+    # too short
+    assert orc.intersect_hit(0, 5, 30, 5, 40, 0, 40, 10) is None
+    # through the shared endpoint of two walls: both report the corner (inclusive ends)
+    assert orc.intersect_hit(0, 0, 10, 10, 5, 5, 5, 20) == (5.0, 5.0)
+    assert orc.intersect_hit(0, 0, 10, 10, 5, 5, 20, 5) == (5.0, 5.0)
+    # degenerate segment
+    assert orc.intersect_hit(0, 0, 10, 0, 5, 5, 5, 5) is None
+
+
+def test_rotate_around_and_distance():
+    x, y = orc.rotate_around(10, 20, 5, 0.0)
+    assert (x, y) == (15.0, 20.0)
+    x, y = orc.rotate_around(0, 0, 2, math.pi / 2)
+    assert abs(x) < 1e-15 and abs(y - 2) < 1e-15
+    assert orc.distance(0, 0, 3, 4) == 5.0
+
+
+def _simple_world():
+    world = orc.World(200, 150)
+    robot = orc.Robot(100, 75, 0)
+    robot.add_device(orc.RangeSensor(position=(8, 0), a=0, max=100, width=0))
+    world.add_robot(robot)
+    return world, robot
+
+
+def test_range_sensor_known_answer():
+    world, robot = _simple_world()
+    world.update()
+    # heading 0 looks along +x: mount at x=108, boundary wall at x=200
+    assert robot[0].get_distance() == pytest.approx(92.0, abs=1e-12)
+    world.add_wall("blue", 150, 0, 150, 150, box=False)
+    world.update()
+    assert robot[0].get_distance() == pytest.approx(42.0, abs=1e-12)
+    # out of range -> max
+    r2 = orc.RangeSensor(position=(8, 0), a=0, max=20, width=0)
+    robot.add_device(r2)
+    world.update()
+    assert r2.get_distance() == 20 and r2.get_reading() == 1.0
+
+
+def test_range_fan_has_three_rays():
+    s = orc.RangeSensor(width=10.0)
+    assert s.ray_count() == 3
+    assert orc.RangeSensor(width=0).ray_count() == 1
+
+
+def test_drive_into_wall_stalls():
+    world, robot = _simple_world()
+    robot.move(1.0, 0.0)
+    stalled_at = None
+    for step in range(200):
+        world.step()
+        if robot.stalled:
+            stalled_at = step
+            break
+    assert stalled_at is not None
+    # front of the box (7.5 ahead of the centre) stops short of the wall at x=200
+    assert robot.x + 7.5 <= 200.0 and robot.x + 7.5 > 200.0 - 2.0 - 1e-9
+    assert robot.vx == 0.0
+    # the stall zeroed the velocity: the robot creeps up again (ramp) but never crosses
+    stalls = 0
+    for _ in range(100):
+        world.step()
+        stalls += robot.stalled
+        assert robot.x + 7.5 <= 200.0
+    assert stalls > 0
+
+
+def test_motion_ramp_and_heading():
+    world, robot = _simple_world()
+    robot.move(1.0, 1.0)
+    world.step()
+    # one step: velocities ramp by ramp*dt = 0.1
+    assert robot.vx == pytest.approx(0.1) and robot.va == pytest.approx(0.1)
+    assert robot.a == pytest.approx(-0.01)
+    assert robot.x == pytest.approx(100 + 0.1 * math.cos(-0.01))
+    assert robot.y == pytest.approx(75 + 0.1 * math.sin(-0.01))
+
+
+def test_light_and_occlusion():
+    world, robot = _simple_world()
+    light = robot.add_device(orc.LightSensor(position=(0, 0)))
+    world.add_bulb("white", 150, 75, 0, 2.0)
+    world.update()
+    assert light.get_brightness() == pytest.approx(2.0 * 1000.0 / 50.0 ** 2)
+    world.add_wall("blue", 120, 0, 120, 150, box=False)
+    world.update()
+    assert light.get_brightness() == 0.0
+
+
+def test_smell_grid_lookup():
+    world, robot = _simple_world()
+    smell = robot.add_device(orc.SmellSensor(position=(0, 0)))
+    world.add_food(100, 75, 20.0)
+    world.update()
+    cs = world.smell_cell_size
+    cx, cy = (int(100 / cs) + 0.5) * cs, (int(75 / cs) + 0.5) * cs
+    d2 = (cx - 100) ** 2 + (cy - 75) ** 2
+    assert smell.get_reading() == pytest.approx(math.exp(-d2 / (2 * 400.0)))
+
+
+def test_camera_columns_known_answer():
+    world = orc.World(200, 200)
+    robot = orc.Robot(100, 100, 0)
+    cam = robot.add_device(orc.Camera(width=8, height=16, a=60))
+    world.add_robot(robot)
+    pic = cam.take_picture()
+    assert len(pic) == 16 and len(pic[0]) == 8
+    # centre column (i = 4, angle 0) looks along +x and hits the purple boundary at distance 100
+    s = 1.0 - 100.0 / 200.0 * 1.0
+    sc = 1.0 - 100.0 / 200.0 * 0.9
+    high = (1 - s) * 16
+    col = [pic[j][4] for j in range(16)]
+    for j in range(16):
+        if j < high / 2:
+            assert col[j] == (0, 0, 128, 255)
+        elif j < 16 - high / 2:
+            assert col[j] == (int(128 * sc), 0, int(128 * sc), 255)
+        else:
+            assert col[j] == (0, 128, 0, 255)
+
+
+def test_camera_sees_other_robot_strip():
+    world = orc.World(200, 200)
+    robot = orc.Robot(50, 100, 0)
+    cam = robot.add_device(orc.Camera(width=8, height=16, a=60))
+    world.add_robot(robot)
+    other = orc.Robot(120, 100, 0, color="blue", height=0.5)
+    world.add_robot(other)
+    pic = cam.take_picture()
+    blues = [pic[j][4] for j in range(16) if pic[j][4][2] > 0 and pic[j][4][0] == 0 and pic[j][4][1] == 0 and pic[j][4][2] != 128]
+    assert len(blues) > 0
+
+
+def test_counted_tests_match_formula():
+    scene = rb.scenes.demo_scene(2)
+    world, devs = sa.build_world(scene, 0)
+    world.counted_tests = 0
+    world.step()
+    for cam in devs["camera"]:
+        cam.take_picture()
+    assert world.counted_tests == scene.slice(0, 1).tests_per_step()
+
+
+@pytest.mark.parametrize("name", ["config1_1000steps.json", "demo_3steps.json"])
+def test_golden_fixtures(name):
+    """The oracle still reproduces the committed golden vectors (tests/golden/make_golden.py)."""
+    with open(os.path.join(GOLDEN, name)) as f:
+        gold = json.load(f)
+    scene = getattr(rb.scenes, gold["generator"])(**gold["kwargs"])
+    for entry in gold["worlds"]:
+        obs = sa.step_and_observe(scene, entry["world"], gold["steps"], camera=False)
+        for key in ("pose", "range", "light", "smell", "stalled"):
+            np.testing.assert_allclose(np.array(obs[key], dtype=np.float64), np.array(entry[key], dtype=np.float64),
+                                       rtol=1e-12, atol=1e-12, err_msg=key)

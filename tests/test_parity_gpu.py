@@ -1,0 +1,151 @@
+# -*- coding: utf-8 -*-
+"""Parity proper: CUDA engine through the C ABI vs the float64 oracle on the
+same seeded scenes (BASELINE.json tolerances are in tests/parity.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import aitk_robots_b200 as rb
+import parity
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_demo_scene_every_device_kind():
+    stats = parity.compare(rb.scenes.demo_scene(32), n_steps=3)
+    assert stats["max_rel_dist"] < 1e-5
+    assert stats["pixel_mismatch"] <= 0.001 * stats["pixels"]
+
+
+def test_config1_trajectory_1000_steps():
+    """Config 1 as written: 1000 World.steps, pose/collision trajectory identical."""
+    scene = rb.scenes.config1(n_worlds=4, seed=1)
+    stats = parity.compare(scene, n_steps=1000)
+    assert stats["max_pose_err"] < 1e-9
+
+
+def test_config1_golden_fixture():
+    with open(os.path.join(GOLDEN, "config1_1000steps.json")) as f:
+        gold = json.load(f)
+    scene = rb.scenes.config1(**gold["kwargs"])
+    out = parity.run_engine(scene, gold["steps"])
+    for entry in gold["worlds"]:
+        i = entry["world"]
+        np.testing.assert_allclose(out["pose"][i], np.array(entry["pose"]), atol=1e-9)
+        np.testing.assert_array_equal(out["stalled"][i], np.array(entry["stalled"]))
+        np.testing.assert_allclose(out["range"][i], np.array(entry["range"]), rtol=1e-4)
+
+
+def test_demo_golden_fixture():
+    with open(os.path.join(GOLDEN, "demo_3steps.json")) as f:
+        gold = json.load(f)
+    scene = rb.scenes.demo_scene(**gold["kwargs"])
+    out = parity.run_engine(scene, gold["steps"])
+    for entry in gold["worlds"]:
+        i = entry["world"]
+        np.testing.assert_allclose(out["pose"][i], np.array(entry["pose"]), atol=1e-9)
+        np.testing.assert_array_equal(out["stalled"][i], np.array(entry["stalled"]))
+        np.testing.assert_allclose(out["range"][i], np.array(entry["range"]), rtol=1e-4)
+        np.testing.assert_allclose(out["light"][i], np.array(entry["light"]), rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(out["smell"][i], np.array(entry["smell"]), rtol=1e-6, atol=1e-9)
+
+
+def test_config2_camera_and_range():
+    scene = rb.scenes.config2(n_worlds=64, cam_w=256, cam_h=128)
+    stats = parity.compare(scene, n_steps=2, worlds=range(0, 64, 8))
+    assert stats["max_rel_dist"] < 1e-5
+    assert stats["pixel_mismatch"] <= 0.001 * stats["pixels"]
+
+
+def test_config3_multi_robot_collisions_and_light():
+    scene = rb.scenes.config3(n_worlds=64)
+    stats = parity.compare(scene, n_steps=20, worlds=range(0, 64, 4), camera=False)
+    assert stats["ranges"] == 16 * 64 and stats["max_rel_dist"] < 1e-5
+
+
+def test_config4_maze_camera():
+    for variant in ("maze", "random"):
+        scene = rb.scenes.config4(n_worlds=32, variant=variant)
+        stats = parity.compare(scene, n_steps=3, worlds=range(0, 32, 4))
+        assert stats["pixel_mismatch"] <= 0.002 * stats["pixels"]
+
+
+@pytest.mark.parametrize("S,rays", [(12, 1), (300, 4), (2000, 1), (1000, 64)])
+def test_config5_sweep_cells(S, rays):
+    scene = rb.scenes.config5(n_worlds=8, n_segments=S, n_rays=rays)
+    stats = parity.compare(scene, n_steps=1, worlds=range(0, 8, 4), camera=False)
+    assert stats["max_rel_dist"] < 1e-5
+
+
+def test_edge_cases_empty_and_ragged():
+    """Worlds with zero walls, ragged segment counts, a robot boxed in."""
+    scene = rb.scenes.config2(n_worlds=8, cam_w=32, cam_h=16)
+    scene.seg_count[:] = [20, 0, 1, 4, 7, 19, 20, 3]
+    stats = parity.compare(scene, n_steps=2)
+    assert stats["worlds"] == 8
+
+
+def test_full_size_properties_config2():
+    """BASELINE size (4096 worlds): size-independent properties instead of the oracle."""
+    scene = rb.scenes.config2(n_worlds=4096)
+    eng = rb.BatchEngine(scene)
+    eng.step()
+    eng.synchronize()
+    rng1 = eng.download("range")
+    cam1 = eng.download("camera")
+    pose1 = eng.download("pose")
+    # idempotence: sensing again without moving reproduces every observation bit for bit
+    eng.step(flags=rb.STEP_SENSE | rb.STEP_CAMERA)
+    eng.synchronize()
+    assert np.array_equal(rng1, eng.download("range"))
+    assert np.array_equal(cam1, eng.download("camera"))
+    assert np.array_equal(pose1, eng.download("pose"))
+    # ranges are bounded by max and positive; every pixel is opaque (walls enclose the room)
+    assert (rng1 > 0).all() and (rng1 <= 100.0).all()
+    assert (cam1[..., 3] == 255).all()
+    # batch independence: world i of the big batch == the same world stepped alone
+    for i in (0, 1777, 4095):
+        alone = parity.run_engine(scene.slice(i, 1), 1)
+        assert np.array_equal(alone["range"][0], rng1[i])
+        assert np.array_equal(alone["camera"][0], cam1[i])
+    # the first image column band is sky, the last ground
+    assert (cam1[:, 0, 0, :, 2] == 128).all() and (cam1[:, 0, -1, :, 1] == 128).all()
+    eng.close()
+
+
+def test_facade_dropin_api():
+    world = rb.World(200, 150)
+    world.add_wall("blue", 150, 0, 150, 150, box=False)
+    robot = rb.Robot(100, 75, 0)
+    robot.add_device(rb.RangeSensor(position=(8, 0), a=0, max=100, width=0))
+    cam = robot.add_device(rb.Camera(width=64, height=32))
+    world.add_robot(robot)
+    world.step()
+    assert robot[0].get_distance() == pytest.approx(42.0, rel=1e-6)
+    pic = cam.take_picture()
+    assert pic.size == (64, 32) and pic.mode == "RGBA"
+    robot.move(1.0, 0.0)
+    for _ in range(5):
+        world.step()
+    assert robot.x > 100 and not robot.stalled
+
+
+def test_zero_copy_tensor_and_bind_output():
+    import torch
+
+    scene = rb.scenes.config2(n_worlds=16, cam_w=32, cam_h=16)
+    eng = rb.BatchEngine(scene)
+    t = eng.tensor("range")
+    eng.step()
+    eng.synchronize()
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), eng.download("range"))
+    ext = torch.zeros((16, 1, 16, 32, 4), dtype=torch.uint8, device="cuda")
+    eng.bind_output("camera", ext)
+    eng.step(flags=rb.STEP_CAMERA)
+    eng.synchronize()
+    assert int(ext[..., 3].min()) == 255
+    eng.bind_output("camera", None)
+    eng.close()
