@@ -147,6 +147,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     for (int k = 0; k < 4; ++k) {
       rdev[r].corner_dist[k] = std::sqrt((0 - cx[k]) * (0 - cx[k]) + (0 - cy[k]) * (0 - cy[k]));
       rdev[r].corner_ang[k] = std::atan2(-cx[k], cy[k]);
+      rdev[r].cox[k] = rdev[r].corner_dist[k] * std::cos(rdev[r].corner_ang[k] + 1.5707963267948966);
+      rdev[r].coy[k] = rdev[r].corner_dist[k] * std::sin(rdev[r].corner_ang[k] + 1.5707963267948966);
     }
     rdev[r].height = d.height;
     rdev[r].vx_ramp = d.vx_ramp;

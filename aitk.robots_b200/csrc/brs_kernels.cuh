@@ -31,6 +31,7 @@ namespace brs {
 struct RobotDev {
   double corner_dist[4];  // distance(0,0,cx,cy) of bbox corner k
   double corner_ang[4];   // atan2(-cx, cy)
+  double cox[4], coy[4];  // corner offset in the a=0 frame: dist * cos/sin(ang + pi/2)
   double height;
   double vx_ramp, vy_ramp, va_ramp;
   uint32_t rgba;
@@ -110,7 +111,7 @@ __host__ __device__ inline SmemLayout make_layout(int seg_cap, int R, int n_came
   L.spose = o; o += R * 3 * 8;
   L.svel = o; o += R * 3 * 8;
   L.rcs = o; o += R * 2 * 8;
-  L.prop = o; o += 16 * 8;  // pbox[8], ppose[3], pvel[3], spare
+  L.prop = o; o += R * 16 * 8;  // per robot: pbox[8], ppose[3], pvel[3], cos/sin of the proposed heading
   L.mbar = o; o += 2 * 8; o = align_up(o, 16);
   L.colinfo = o; o += n_camera * cam_w * (int)sizeof(ColInfo);
   int strips_per_col = 4 * (R - 1);
@@ -297,19 +298,20 @@ __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInf
   ColInfo ci[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) ci[k] = cinf[4 * q + k];
-  const bool any_strip = (ci[0].n_robot | ci[1].n_robot | ci[2].n_robot | ci[3].n_robot) != 0;
-  for (int j = r0; j < H; j += rstep) {
+  // rare per-quad extras (robot strips, a column without any wall hit) take a slow path
+  const bool slow = ((ci[0].n_robot | ci[1].n_robot | ci[2].n_robot | ci[3].n_robot) != 0) ||
+                    ((ci[0].top | ci[1].top | ci[2].top | ci[3].top) < 0);
+  uint4* o = out + (size_t)r0 * Q + q;
+  const size_t ostep = (size_t)rstep * Q;
+  for (int j = r0; j < H; j += rstep, o += ostep) {
     const uint32_t sky = rowsky[j], gnd = rowgnd[j];
     uint32_t px[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t v = j < ci[k].top ? sky : (j < ci[k].bot ? ci[k].rgba : gnd);
-      if (ci[k].top < 0) v = 0u;  // no wall hit: the column keeps the blank RGBA (0,0,0,0)
-      px[k] = v;
-    }
-    if (any_strip) {
+    for (int k = 0; k < 4; ++k) px[k] = j < ci[k].top ? sky : (j < ci[k].bot ? ci[k].rgba : gnd);
+    if (slow) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        if (ci[k].top < 0) px[k] = 0u;  // no wall hit: the column keeps the blank RGBA (0,0,0,0)
         const Strip* st = strips + (size_t)(4 * q + k) * strips_per_col;
         float best = 3.0e38f;
         for (int n = 0; n < ci[k].n_robot; ++n) {
@@ -323,14 +325,14 @@ __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInf
         }
       }
     }
-    __stcs(out + (size_t)j * Q + q, make_uint4(px[0], px[1], px[2], px[3]));
+    __stcs(o, make_uint4(px[0], px[1], px[2], px[3]));
   }
 }
 
 // ------------------------------------------------------------------------------
 // The fused World.step kernel
 // ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) brs_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(320, 3) brs_step_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, T = blockDim.x;
   const int R = p.n_robots, SC = p.seg_cap;
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(512) brs_step_kernel(const __grid_constant__ K
   double* const spose = (double*)(smem + L.spose);
   double* const svel = (double*)(smem + L.svel);
   double* const rcs = (double*)(smem + L.rcs);
-  double* const prop = (double*)(smem + L.prop);  // pbox[0..7], ppose[8..10], pvel[11..13]
+  double* const prop = (double*)(smem + L.prop);  // per robot 16: pbox[0..7], ppose[8..10], pvel[11..13], cos, sin
   uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
   ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
   Strip* const strips = (Strip*)(smem + L.strips);
@@ -384,19 +386,40 @@ __global__ void __launch_bounds__(512) brs_step_kernel(const __grid_constant__ K
       }
     }
     const int S = min(p.seg_count[w], SC);
-    // robot state -> shared (float64)
-    if (tid < R * 3) {
-      spose[tid] = p.pose[(size_t)w * R * 3 + tid];
-      svel[tid] = p.vel[(size_t)w * R * 3 + tid];
-    }
-    __syncthreads();
-    // committed bounding boxes: corner k of robot r (compute_boundingbox)
-    if (tid < R * 4) {
-      const int r = tid >> 2, k = tid & 3;
+    // ---------------- phase 1: Robot.step for every robot ----------------------
+    // 1a. one thread per robot: state -> shared, heading trig of the committed
+    //     pose, and (a robot's proposal depends on nothing but itself) the
+    //     proposed pose / velocities.  One sincos pair per robot per step.
+    if (tid < R) {
+      const int r = tid;
       const RobotDev& rd = p.robots[r];
-      const double th = da(da(spose[r * 3 + 2], rd.corner_ang[k]), BRS_PI_OVER_2);
-      dbox[r * 8 + 2 * k] = da(spose[r * 3 + 0], dm(rd.corner_dist[k], cos(-th)));
-      dbox[r * 8 + 2 * k + 1] = ds(spose[r * 3 + 1], dm(rd.corner_dist[k], sin(-th)));
+      const size_t o = ((size_t)w * R + r) * 3;
+      const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
+      const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
+      spose[3 * r] = x; spose[3 * r + 1] = y; spose[3 * r + 2] = a;
+      svel[3 * r] = v0; svel[3 * r + 1] = v1; svel[3 * r + 2] = v2;
+      double sn0, cs0;
+      sincos(a, &sn0, &cs0);
+      rcs[2 * r] = cs0;
+      rcs[2 * r + 1] = sn0;
+      if (do_move) {
+        const double* tv = p.tvel + o;
+        const double vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
+        const double vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
+        const double va = deltav(tv[2], v2, rd.va_ramp, p.dt);
+        const double pa = ds(a, dm(va, p.dt));
+        const double ang = da(-pa, BRS_PI_OVER_2);
+        double sn, cs;
+        sincos(ang, &sn, &cs);
+        // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
+        const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
+        const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
+        double* pr = prop + 16 * r;
+        pr[8] = da(x, tvx); pr[9] = da(y, tvy); pr[10] = pa;
+        pr[11] = vx; pr[12] = vy; pr[13] = va;
+        pr[14] = sn;  // sin(pi/2 - pa) = cos(pa)
+        pr[15] = cs;  // cos(pi/2 - pa) = sin(pa)
+      }
     }
     mbar_wait(smem_u32(&mbar[buf]), parity);
     const uint32_t* raw = rawbuf[buf];
@@ -407,44 +430,38 @@ __global__ void __launch_bounds__(512) brs_step_kernel(const __grid_constant__ K
       segtab[j] = make_float4(x1, y1, x2 - x1, y2 - y1);
     }
     __syncthreads();
-
-    // ---------------- phase 1: Robot.step for every robot, in order -----------
+    // 1b. bounding-box corners (compute_boundingbox) of the committed and of the
+    //     proposed pose: corner = centre + R(heading) * (corner offset in the a=0 frame)
+    if (tid < R * 4) {
+      const int r = tid >> 2, k = tid & 3;
+      const RobotDev& rd = p.robots[r];
+      const double ox = rd.cox[k], oy = rd.coy[k];
+      const double c0 = rcs[2 * r], s0 = rcs[2 * r + 1];
+      dbox[r * 8 + 2 * k] = da(spose[3 * r], ds(dm(c0, ox), dm(s0, oy)));
+      dbox[r * 8 + 2 * k + 1] = da(spose[3 * r + 1], da(dm(s0, ox), dm(c0, oy)));
+      if (do_move) {
+        double* pr = prop + 16 * r;
+        const double c1 = pr[14], s1 = pr[15];
+        pr[2 * k] = da(pr[8], ds(dm(c1, ox), dm(s1, oy)));
+        pr[2 * k + 1] = da(pr[9], da(dm(s1, ox), dm(c1, oy)));
+      }
+    }
+    __syncthreads();
+    // 1c. collision tests in list order: robot i sees the already-moved boxes of
+    //     the robots before it.  FP64, decisions equal the float64 reference's.
     if (do_move) {
       for (int i = 0; i < R; ++i) {
-        if (tid < 4) {
-          const RobotDev& rd = p.robots[i];
-          const double x = spose[i * 3], y = spose[i * 3 + 1], a = spose[i * 3 + 2];
-          const double* tv = p.tvel + ((size_t)w * R + i) * 3;
-          const double vx = deltav(tv[0], svel[i * 3 + 0], rd.vx_ramp, p.dt);
-          const double vy = deltav(tv[1], svel[i * 3 + 1], rd.vy_ramp, p.dt);
-          const double va = deltav(tv[2], svel[i * 3 + 2], rd.va_ramp, p.dt);
-          const double pa = ds(a, dm(va, p.dt));
-          const double ang = da(-pa, BRS_PI_OVER_2);
-          const double sn = sin(ang), cs = cos(ang);
-          // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
-          const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
-          const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
-          const double px = da(x, tvx), py = da(y, tvy);
-          const int k = tid;
-          const double th = da(da(pa, rd.corner_ang[k]), BRS_PI_OVER_2);
-          prop[2 * k] = da(px, dm(rd.corner_dist[k], cos(-th)));
-          prop[2 * k + 1] = ds(py, dm(rd.corner_dist[k], sin(-th)));
-          if (tid == 0) {
-            prop[8] = px; prop[9] = py; prop[10] = pa;
-            prop[11] = vx; prop[12] = vy; prop[13] = va;
-          }
-        }
-        __syncthreads();
+        const double* pr = prop + 16 * i;
         int hit = 0;
         {
           double ex1[4], ey1[4], edx[4], edy[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int e2 = (e + 1) & 3;
-            ex1[e] = prop[2 * e];
-            ey1[e] = prop[2 * e + 1];
-            edx[e] = ds(prop[2 * e2], prop[2 * e]);
-            edy[e] = ds(prop[2 * e2 + 1], prop[2 * e + 1]);
+            ex1[e] = pr[2 * e];
+            ey1[e] = pr[2 * e + 1];
+            edx[e] = ds(pr[2 * e2], pr[2 * e]);
+            edy[e] = ds(pr[2 * e2 + 1], pr[2 * e + 1]);
           }
           const int nseg = S + 4 * R;
           for (int j = tid; j < nseg; j += T) {
@@ -456,40 +473,42 @@ __global__ void __launch_bounds__(512) brs_step_kernel(const __grid_constant__ K
           }
         }
         hit = __syncthreads_or(hit);
-        if (!hit) {
-          if (tid < 8) dbox[i * 8 + tid] = prop[tid];
-          if (tid < 3) {
-            spose[i * 3 + tid] = prop[8 + tid];
-            svel[i * 3 + tid] = prop[11 + tid];
+        // commit or stall; every consumer below reads stable sources (old dbox or prop)
+        if (tid < 4) {  // this robot's box as FP32 search segments for the sensors
+          const int e = tid, e2 = (e + 1) & 3;
+          const double* src = hit ? dbox + i * 8 : pr;
+          const float x1 = (float)src[2 * e], y1 = (float)src[2 * e + 1];
+          const float x2 = (float)src[2 * e2], y2 = (float)src[2 * e2 + 1];
+          segtab[S + 4 * i + e] = make_float4(x1, y1, x2 - x1, y2 - y1);
+        }
+        if (tid < 3) {
+          const size_t o = ((size_t)w * R + i) * 3 + tid;
+          if (!hit) {
+            p.pose[o] = pr[8 + tid];
+            p.vel[o] = pr[11 + tid];
+          } else {
+            p.vel[o] = 0.0;
           }
-        } else if (tid < 3) {
-          svel[i * 3 + tid] = 0.0;
         }
         if (tid == 0) p.stalled[(size_t)w * R + i] = (uint8_t)(hit ? 1 : 0);
-        __syncthreads();
+        // (__syncthreads_or was a barrier: nobody is still testing against dbox)
+        if (!hit) {
+          if (tid < 8) dbox[i * 8 + tid] = pr[tid];
+          if (tid < 3) spose[i * 3 + tid] = pr[8 + tid];
+          if (tid == 8) { rcs[2 * i] = pr[14]; rcs[2 * i + 1] = pr[15]; }
+        }
+        __syncthreads();  // robot i+1's tests and the sensors read dbox / spose / rcs
       }
-      if (tid < R * 3) {
-        p.pose[(size_t)w * R * 3 + tid] = spose[tid];
-        p.vel[(size_t)w * R * 3 + tid] = svel[tid];
-      }
+    } else if (tid < R * 4) {
+      const int r = tid >> 2, e = tid & 3, e2 = (e + 1) & 3;
+      const float x1 = (float)dbox[r * 8 + 2 * e], y1 = (float)dbox[r * 8 + 2 * e + 1];
+      const float x2 = (float)dbox[r * 8 + 2 * e2], y2 = (float)dbox[r * 8 + 2 * e2 + 1];
+      segtab[S + tid] = make_float4(x1, y1, x2 - x1, y2 - y1);
     }
 
     // ---------------- phase 2: ray-cast sensors --------------------------------
     if (do_sense || do_cam) {
-      // robot boxes as FP32 search segments, per-robot cos/sin of the heading
-      if (tid < R * 4) {
-        const int r = tid >> 2, e = tid & 3, e2 = (e + 1) & 3;
-        const float x1 = (float)dbox[r * 8 + 2 * e], y1 = (float)dbox[r * 8 + 2 * e + 1];
-        const float x2 = (float)dbox[r * 8 + 2 * e2], y2 = (float)dbox[r * 8 + 2 * e2 + 1];
-        segtab[S + tid] = make_float4(x1, y1, x2 - x1, y2 - y1);
-      }
-      if (tid < R) {
-        double sn, cs;
-        sincos(spose[tid * 3 + 2], &sn, &cs);
-        rcs[tid * 2] = cs;
-        rcs[tid * 2 + 1] = sn;
-      }
-      __syncthreads();
+      if (!do_move) __syncthreads();
       const double wsize = (double)fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]);
 
       if (tid < p.TA) {
