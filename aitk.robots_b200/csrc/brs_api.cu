@@ -145,10 +145,11 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     const double cx[4] = {d.bbox[0], d.bbox[0], d.bbox[1], d.bbox[1]};
     const double cy[4] = {d.bbox[3], d.bbox[2], d.bbox[2], d.bbox[3]};
     for (int k = 0; k < 4; ++k) {
-      rdev[r].corner_dist[k] = std::sqrt((0 - cx[k]) * (0 - cx[k]) + (0 - cy[k]) * (0 - cy[k]));
-      rdev[r].corner_ang[k] = std::atan2(-cx[k], cy[k]);
-      rdev[r].cox[k] = rdev[r].corner_dist[k] * std::cos(rdev[r].corner_ang[k] + 1.5707963267948966);
-      rdev[r].coy[k] = rdev[r].corner_dist[k] * std::sin(rdev[r].corner_ang[k] + 1.5707963267948966);
+      // compute_boundingbox: dist = distance(0,0,cx,cy), ang = atan2(-cx, cy), swung by ang + pi/2
+      const double dist = std::sqrt((0 - cx[k]) * (0 - cx[k]) + (0 - cy[k]) * (0 - cy[k]));
+      const double ang = std::atan2(-cx[k], cy[k]);
+      rdev[r].cox[k] = dist * std::cos(ang + 1.5707963267948966);
+      rdev[r].coy[k] = dist * std::sin(ang + 1.5707963267948966);
     }
     rdev[r].height = d.height;
     rdev[r].vx_ramp = d.vx_ramp;
@@ -262,14 +263,13 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   const int nother = cfg->n_range + cfg->n_light + cfg->n_smell;
   e->TA = ncols ? std::min((ncols + 31) / 32 * 32, 256) : 0;
   if (nother == 0)
-    e->TB = 0;
+    e->TB = 32;  // the helper warp (prepares the next world) always exists
   else if (e->TA)
     e->TB = nother > 8 ? 64 : 32;
   else
     e->TB = std::min(std::max((nother + 31) / 32 * 32, 32), 256);
   // small worlds with few rays: still give the motion phase a full warp
-  e->T = std::max(e->TA + e->TB, 32);
-  if (e->TB == 0 && e->TA == 0) e->TB = 0;
+  e->T = e->TA + e->TB;
   e->SL = nother ? std::min(32, pow2floor(std::max(e->TB / nother, 1))) : 1;
   const SmemLayout L = make_layout(cfg->seg_cap, R, cfg->n_camera, e->cam_w, e->cam_h);
   e->smem = L.total;
