@@ -45,16 +45,31 @@ struct brs_engine {
   CameraDev* d_cameras = nullptr;
   PointDev* d_lights = nullptr;
   PointDev* d_smells = nullptr;
+  GroupDev* d_groups = nullptr;
+  int* d_gr_idx = nullptr;
+  int* d_dr_idx = nullptr;
   double2* d_camcs = nullptr;
   uint32_t* d_rowsky = nullptr;
   uint32_t* d_rowgnd = nullptr;
-  int T = 32, TA = 0, TB = 0, SL = 1, grid = 1, smem = 0;
+  unsigned int* d_sched = nullptr;
+  int n_group = 0, n_gr = 0, n_dr = 0;
+  // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
+  int T = 256, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
 };
 
 static int pow2floor(int x) {
   int p = 1;
   while (p * 2 <= x) p *= 2;
   return p;
+}
+static int pow2ceil(int x) {
+  int p = 1;
+  while (p < x) p *= 2;
+  return p;
+}
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
 }
 
 extern "C" int brs_abi_version(void) { return BRS_ABI_VERSION; }
@@ -151,6 +166,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       rdev[r].cox[k] = dist * std::cos(ang + 1.5707963267948966);
       rdev[r].coy[k] = dist * std::sin(ang + 1.5707963267948966);
     }
+    rdev[r].radius = 0;
+    for (int k = 0; k < 4; ++k) rdev[r].radius = std::fmax(rdev[r].radius, std::hypot(cx[k], cy[k]));
     rdev[r].height = d.height;
     rdev[r].vx_ramp = d.vx_ramp;
     rdev[r].vy_ramp = d.vy_ramp;
@@ -184,6 +201,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       n = 1;
     }
     g.n_rays = n;
+    g.group = -1;
     e->ranges[i].n_rays = n;
     e->rays_range += n;
   }
@@ -217,6 +235,44 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     return v;
   };
   std::vector<PointDev> ldev = points(e->lights), sdev = points(e->smells);
+  // ---- origin groups: rays that leave one mount point of one robot share a
+  // per-(origin, segment) table.  Every camera gets one; range sensors join when
+  // the mount carries a camera or at least BRS_GROUP_MIN rays in total.
+  std::vector<GroupDev> groups;
+  auto find_group = [&](int robot, double mx, double my) {
+    for (size_t k = 0; k < groups.size(); ++k)
+      if (groups[k].robot == robot && groups[k].mx == mx && groups[k].my == my) return (int)k;
+    return -1;
+  };
+  auto add_group = [&](int robot, double mx, double my) {
+    int k = find_group(robot, mx, my);
+    if (k < 0) {
+      GroupDev g;
+      g.robot = robot; g._pad = 0; g.mx = mx; g.my = my;
+      groups.push_back(g);
+      k = (int)groups.size() - 1;
+    }
+    return k;
+  };
+  for (auto& c : cdev) c.group = add_group(c.robot, c.mx, c.my);
+  {
+    const int group_min = env_int("BRS_GROUP_MIN", 4);
+    for (auto& g : gdev) {
+      int k = find_group(g.robot, g.mx, g.my);
+      if (k < 0) {
+        int rays = 0;  // range rays leaving this mount
+        for (auto& h : gdev)
+          if (h.robot == g.robot && h.mx == g.mx && h.my == g.my) rays += h.n_rays;
+        if (rays >= group_min) k = add_group(g.robot, g.mx, g.my);
+      }
+      g.group = k;
+    }
+  }
+  std::vector<int> gr_idx, dr_idx;
+  for (int i = 0; i < cfg->n_range; ++i) (gdev[i].group >= 0 ? gr_idx : dr_idx).push_back(i);
+  e->n_group = (int)groups.size();
+  e->n_gr = (int)gr_idx.size();
+  e->n_dr = (int)dr_idx.size();
   std::vector<uint32_t> rowsky(std::max(e->cam_h, 1)), rowgnd(std::max(e->cam_h, 1));
   for (int j = 0; j < e->cam_h; ++j) {
     const double horizon = e->cam_h / 2.0;
@@ -230,6 +286,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   if ((rc = to_device(&e->d_robots, rdev)) || (rc = to_device(&e->d_ranges, gdev)) ||
       (rc = to_device(&e->d_cameras, cdev)) || (rc = to_device(&e->d_lights, ldev)) ||
       (rc = to_device(&e->d_smells, sdev)) || (rc = to_device(&e->d_camcs, camcs)) ||
+      (rc = to_device(&e->d_groups, groups)) || (rc = to_device(&e->d_gr_idx, gr_idx)) ||
+      (rc = to_device(&e->d_dr_idx, dr_idx)) ||
       (rc = to_device(&e->d_rowsky, rowsky)) || (rc = to_device(&e->d_rowgnd, rowgnd))) {
     brs_destroy(e);
     return rc;
@@ -259,32 +317,62 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   }
 
   // ---- launch geometry -------------------------------------------------------
+  // Tiles of TW consecutive worlds per CTA pass; TW is sized so that a tile offers
+  // about one ray task per thread within a shared-memory budget that keeps
+  // several CTAs resident per SM (different CTAs sit in different phases, which
+  // overlaps the FP32 search of one with the HBM stores of another).
+  {
+    cudaError_t ce = cudaMalloc((void**)&e->d_sched, 16);
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_sched, 0, 16);
+    if (ce != cudaSuccess) {
+      brs_destroy(e);
+      return fail(BRS_ERR_CUDA, std::string("brs_create: scheduler allocation failed: ") + cudaGetErrorString(ce));
+    }
+  }
   const int ncols = cfg->n_camera * e->cam_w;
-  const int nother = cfg->n_range + cfg->n_light + cfg->n_smell;
-  e->TA = ncols ? std::min((ncols + 31) / 32 * 32, 256) : 0;
-  if (nother == 0)
-    e->TB = 32;  // the helper warp (prepares the next world) always exists
-  else if (e->TA)
-    e->TB = nother > 8 ? 64 : 32;
-  else
-    e->TB = std::min(std::max((nother + 31) / 32 * 32, 32), 256);
-  // small worlds with few rays: still give the motion phase a full warp
-  e->T = e->TA + e->TB;
-  e->SL = nother ? std::min(32, pow2floor(std::max(e->TB / nother, 1))) : 1;
-  const SmemLayout L = make_layout(cfg->seg_cap, R, cfg->n_camera, e->cam_w, e->cam_h);
-  e->smem = L.total;
+  e->NR = env_int("BRS_NR", ncols >= 64 ? 2 : 1);
+  if (e->NR != 1 && e->NR != 2 && e->NR != 4) e->NR = 1;
+  if (e->cam_w % std::max(e->NR, 1)) e->NR = 1;
+  const int gtasks = ncols / e->NR + e->n_gr;
+  const int dtasks = e->n_dr + cfg->n_light + cfg->n_smell;
+  const int tasks = std::max(gtasks + dtasks, 1);
+  e->T = env_int("BRS_NT", 256);
+  if (e->T != 64 && e->T != 128 && e->T != 256) e->T = 256;
+  auto smem_for = [&](int tw) { return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h).total; };
+  const int budget = env_int("BRS_SMEM_BUDGET", 72 * 1024);
+  int tw = std::max(1, (e->T + tasks - 1) / tasks);
+  tw = std::min(tw, 64);
+  // keep at least ~4 tiles per resident CTA slot so that the dynamic scheduler can balance
+  tw = std::min(tw, std::max(1, cfg->n_worlds / (e->sm_count * 8)));
+  while (tw > 1 && smem_for(tw) > budget) --tw;
+  tw = env_int("BRS_TW", tw);
+  tw = std::max(1, std::min(tw, cfg->n_worlds));
+  e->TW = tw;
+  e->smem = smem_for(tw);
   if ((size_t)e->smem > prop.sharedMemPerBlockOptin) {
     brs_destroy(e);
-    return fail(BRS_ERR_UNSUPPORTED, "brs_create: world too large for one CTA's shared memory (seg_cap / camera width)");
+    return fail(BRS_ERR_UNSUPPORTED, "brs_create: world too large for one CTA's shared memory (seg_cap / camera width / groups)");
   }
-  cudaError_t ce = cudaFuncSetAttribute(brs_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem);
+  e->n_tiles = (cfg->n_worlds + tw - 1) / tw;
+  e->GS = std::min(e->T, std::max(8, pow2ceil(cfg->seg_cap)));
+  e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->T / (gtasks * tw), 1))) : 1;
+  e->SLD = dtasks ? std::min(32, pow2floor(std::max(e->T / (dtasks * tw), 1))) : 1;
+  {
+    const int Q = std::max(e->cam_w / 4, 1);
+    const int slots = std::max(e->T / Q, 1);
+    const int nislot = std::max(1, std::min(tw * std::max(cfg->n_camera, 1), slots));
+    e->paint_rs = std::max(1, slots / nislot);
+  }
+  const void* kfn = e->NR == 4 ? (const void*)brs_step_kernel<4> : e->NR == 2 ? (const void*)brs_step_kernel<2> : (const void*)brs_step_kernel<1>;
+  cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem);
   int nb = 0;
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, brs_step_kernel, e->T, e->smem);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, e->T, e->smem);
   if (ce != cudaSuccess || nb < 1) {
     brs_destroy(e);
     return fail(BRS_ERR_CUDA, std::string("brs_create: kernel does not fit: ") + cudaGetErrorString(ce));
   }
-  e->grid = std::min(cfg->n_worlds, nb * e->sm_count);
+  nb = std::min(nb, env_int("BRS_MAX_CTAS_PER_SM", 32));
+  e->grid = std::max(1, std::min(e->n_tiles, nb * e->sm_count));
   *out = e;
   return BRS_OK;
 }
@@ -299,6 +387,10 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_cameras);
   cudaFree(e->d_lights);
   cudaFree(e->d_smells);
+  cudaFree(e->d_groups);
+  cudaFree(e->d_gr_idx);
+  cudaFree(e->d_dr_idx);
+  cudaFree(e->d_sched);
   cudaFree(e->d_camcs);
   cudaFree(e->d_rowsky);
   cudaFree(e->d_rowgnd);
@@ -363,7 +455,9 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.grid_w = c.grid_w; p.grid_h = c.grid_h;
   p.n_range = c.n_range; p.n_camera = c.n_camera; p.n_light = c.n_light; p.n_smell = c.n_smell;
   p.cam_w = e->cam_w; p.cam_h = e->cam_h;
-  p.TA = e->TA; p.TB = e->TB; p.SL = e->SL;
+  p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
+  p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.paint_rs = e->paint_rs;
+  p.cull_margin = 0.05f;
   p.flags = flags;
   p.dt = time_step; p.smell_cell = c.smell_cell_size; p.light_mult = c.light_multiplier;
   p.seg = (const uint32_t*)e->buf[BRS_BUF_SEG];
@@ -381,8 +475,15 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.smell_out = (float*)cur(e, BRS_BUF_SMELL);
   p.robots = e->d_robots; p.ranges = e->d_ranges; p.cameras = e->d_cameras;
   p.lights = e->d_lights; p.smells = e->d_smells;
+  p.groups = e->d_groups; p.gr_idx = e->d_gr_idx; p.dr_idx = e->d_dr_idx;
   p.cam_cs = e->d_camcs; p.row_sky = e->d_rowsky; p.row_gnd = e->d_rowgnd;
-  brs_step_kernel<<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
+  p.sched = e->d_sched;
+  if (e->NR == 4)
+    brs_step_kernel<4><<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
+  else if (e->NR == 2)
+    brs_step_kernel<2><<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
+  else
+    brs_step_kernel<1><<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
   CK(cudaGetLastError());
   return BRS_OK;
 }

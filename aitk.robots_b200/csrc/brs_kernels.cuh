@@ -1,31 +1,36 @@
 // brs_kernels.cuh -- sm_100a kernels of the batched World.step engine.
 //
-// One persistent CTA steps one world at a time (grid = SMs x resident CTAs,
-// worlds strided over the grid).  The CTA is warp-specialised and software
-// pipelined across worlds:
+// One persistent CTA steps a TILE of TW consecutive worlds at a time; tiles are
+// handed out by a global atomic counter (dynamic scheduling, no tail).  Every
+// phase of World.step runs data-parallel over the whole tile, so barriers and
+// per-world set-up are amortised over TW worlds and all threads work in every
+// phase whatever the shape of a single world:
 //
-//   helper warp (first warp of pool B)         pool A warps (camera columns)
-//   ------------------------------------       ------------------------------
-//   range / light / smell sensors of world w   camera rays of world w
-//   PREPARE world w+1:                         (named barrier, pool A only)
-//     wait its TMA-landed wall store           paint world w's pictures
-//     robot state HBM -> smem, sincos,
-//     proposed poses, box corners (FP64),
-//     FP32 search table
-//   ------------------------------ __syncthreads ------------------------------
-//   all warps: collision tests of world w+1 (FP64), commit / stall
+//   0. TMA     the tile's wall store (SoA rows x1|y1|x2|y2|rgba, TW*20*cap
+//              contiguous bytes) lands in shared memory through ONE bulk copy
+//              (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered and
+//              issued one tile ahead;
+//   1. PREP    thread per (world, robot): FP64 pose proposal, committed and
+//              proposed box corners; all threads: FP32 segment table;
+//   2. COLLIDE thread per (world, robot, wall): conservative FP32 disc cull, then
+//              the exact FP64 4-edge test (IEEE ops, no FMA contraction:
+//              decisions equal the float64 reference's); robot-vs-robot pairs
+//              in both orders so that the list-order dependence of Robot.step
+//              reduces to bit masks;
+//   3. COMMIT  thread per (world, robot): resolve the masks in list order, commit
+//              or stall, write pose / velocity / stalled;
+//   4. TABLE   rays that share an origin (all columns of a Camera, range sensors
+//              on one mount) get a per-(origin, segment) table m = n/na, q = d/na
+//              that makes the inner test division free:
+//                  1/t = m . r      u/t = r x q      hit: 0 <= u/t <= 1/t, 1/t >= 1
+//   5. SENSE   thread per ray (or SL lanes per ray when a tile has few rays):
+//              FP32 nearest-hit search (4 FP32 + 2 compares + 2 selects per test),
+//              warp-shuffle reduction over the SL lanes, then ONE FP64 refinement
+//              of the winning segment so distances and pixel rounding follow the
+//              float64 reference;
+//   6. PAINT   Camera.take_picture: the tile's pictures are one contiguous HBM
+//              block, written with coalesced 16-byte (4 x uchar4) streaming stores.
 //
-//   0. wall stores (SoA rows x1|y1|x2|y2|rgba) arrive in shared memory through
-//      TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered
-//      and issued one world ahead of the prepare step;
-//   1. Robot.step: FP64 pose integration and 4-edge x segment collision tests
-//      (exact IEEE ops, no FMA contraction: decisions equal the float64
-//      reference's);
-//   2. ray-cast sensors: FP32 nearest-hit search (lanes stride over segments,
-//      warp-shuffle min), then one FP64 refinement of the winning segment per
-//      ray so distances and pixel rounding match float64;
-//   3. Camera.take_picture: columns painted with coalesced 16-byte (4 x uchar4)
-//      streaming stores.
 // Tensor cores are unused on purpose: the work is FP32 cross products with no
 // dense contraction (BASELINE.json north_star).
 //
@@ -44,17 +49,19 @@ struct RobotDev {
   double cox[4], coy[4];  // bbox corner k in the a=0 frame: dist_k * cos/sin(atan2(-cx, cy) + pi/2)
   double height;
   double vx_ramp, vy_ramp, va_ramp;
+  double radius;  // circumradius of the box (collision cull)
   uint32_t rgba;
   uint32_t _pad;
 };
 struct RangeDev {
   int robot, n_rays;
+  int group, _pad;      // origin group (shared-origin table) or -1: direct path
   double mx, my;        // mount offset in the a=0 frame: dfc*cos(dir+pi/2), dfc*sin(dir+pi/2)
   double cr[3], sr[3];  // cos/sin(sensor.a - incr_k)
   double max;
 };
 struct CameraDev {
-  int robot, width, height, _pad;
+  int robot, width, height, group;
   double mx, my;
   double max_range, color_fade, size_fade;
 };
@@ -62,14 +69,24 @@ struct PointDev {
   int robot, _pad;
   double mx, my;
 };
+struct GroupDev {  // rays sharing one origin: robot + mount offset
+  int robot, _pad;
+  double mx, my;
+};
 
 struct KParams {
   int n_worlds, n_robots, seg_cap, n_bulbs, grid_w, grid_h;
-  int n_range, n_camera, n_light, n_smell;
+  int n_range, n_camera, n_light, n_smell, n_group;
   int cam_w, cam_h;
-  int TA, TB, SL;  // camera-column threads, other-sensor threads, lanes per other-sensor ray
+  int TW;            // worlds per tile
+  int n_tiles;
+  int GS;            // threads per (world, robot) in the wall-collision phase (power of two)
+  int SLG, SLD;      // lanes per ray task: group path, direct path (powers of two <= 32)
+  int n_gr, n_dr;    // range sensors on the group path / on the direct path
+  int paint_rs;      // row slots of the paint phase
   unsigned flags;
   double dt, smell_cell, light_mult;
+  float cull_margin;
   const uint32_t* seg;      // [B][5][seg_cap]
   const int* seg_count;     // [B]
   const float* world_size;  // [B][2]
@@ -88,9 +105,13 @@ struct KParams {
   const CameraDev* cameras;
   const PointDev* lights;
   const PointDev* smells;
+  const GroupDev* groups;
+  const int* gr_idx;        // [n_gr] range sensors on the group path
+  const int* dr_idx;        // [n_dr] range sensors on the direct path
   const double2* cam_cs;    // [n_camera][cam_w] cos/sin of the column angle i/W*fov - fov/2
   const uint32_t* row_sky;  // [cam_h] rgba per image row
   const uint32_t* row_gnd;  // [cam_h]
+  unsigned int* sched;      // [2] next tile, finished CTAs (self-resetting)
 };
 
 // per-column paint record
@@ -106,36 +127,43 @@ struct __align__(16) Strip {
   float dist;
 };
 
-// per-world working state in shared memory, double buffered (prepared one world ahead)
-//   doubles per robot: pose[3] vel[3] rcs[2] dbox[8] prop[16] = 32
+// per-(world, robot) working state in shared memory, doubles:
+//   pose[3] vel[3] rcs[2] dbox[8] prop[16] = 32
 #define BRS_WS_POSE 0
 #define BRS_WS_VEL 3
 #define BRS_WS_RCS 6
 #define BRS_WS_DBOX 8
 #define BRS_WS_PROP 16
 #define BRS_WS_STRIDE 32
+// prop: [0..8) proposed box corners, [8..11) proposed pose, [11..14) proposed velocity, [14..16) cos/sin
 
 // shared memory carve-up, byte offsets; mirrored on the host for the launch size
 struct SmemLayout {
-  int raw[2], segtab[2], ws[2], meta[2], mbar, colinfo, strips, camcs, rowsky, rowgnd, total;
+  int raw[2], segtab, gtab, ws, org, cflag, meta, colinfo, strips, camcs, rowsky, rowgnd, mbar, sched, total;
 };
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline SmemLayout make_layout(int seg_cap, int R, int n_camera, int cam_w, int cam_h) {
+__host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, int n_group, int n_camera, int cam_w,
+                                                  int cam_h) {
   SmemLayout L;
+  const int nvis = seg_cap + 4 * R;
   int o = 0;
-  for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += 5 * seg_cap * 4; o = align_up(o, 128); }
-  for (int b = 0; b < 2; ++b) { L.segtab[b] = o; o += (seg_cap + 4 * R) * 16; }
-  for (int b = 0; b < 2; ++b) { L.ws[b] = o; o += R * BRS_WS_STRIDE * 8; }
-  for (int b = 0; b < 2; ++b) { L.meta[b] = o; o += 16; }  // int S; float wsize
-  L.mbar = o; o += 2 * 8;
+  for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += TW * 5 * seg_cap * 4; o = align_up(o, 128); }
+  L.segtab = o; o += TW * nvis * 16;
+  L.gtab = o; o += TW * n_group * nvis * 16;
+  L.ws = o; o += TW * R * BRS_WS_STRIDE * 8;
+  L.org = o; o += TW * (n_group > 0 ? n_group : 1) * 16;
+  L.cflag = o; o += TW * R * 16;  // wall hit, pair_old mask, pair_new mask, stalled
+  L.meta = o; o += TW * 8;        // int S; float world extent
   o = align_up(o, 16);
-  L.colinfo = o; o += n_camera * cam_w * (int)sizeof(ColInfo);
-  int strips_per_col = 4 * (R - 1);
-  L.strips = o; o += n_camera * cam_w * strips_per_col * (int)sizeof(Strip);
+  L.colinfo = o; o += TW * n_camera * cam_w * (int)sizeof(ColInfo);
+  L.strips = o; o += TW * n_camera * cam_w * 4 * (R - 1) * (int)sizeof(Strip);
   o = align_up(o, 16);
   L.camcs = o; o += n_camera * cam_w * 16;
   L.rowsky = o; o += cam_h * 4;
   L.rowgnd = o; o += cam_h * 4;
+  o = align_up(o, 8);
+  L.mbar = o; o += 2 * 8;
+  L.sched = o; o += 16;
   L.total = align_up(o, 16);
   return L;
 }
@@ -160,11 +188,19 @@ __device__ __forceinline__ bool isect64(double x1, double y1, double x2, double 
   const double d13y = ds(y1, y3), d13x = ds(x1, x3);
   const double na = ds(dm(d43x, d13y), dm(d43y, d13x));
   const double nb = ds(dm(d21x, d13y), dm(d21y, d13x));
-  // ua = na/den in [0,1] and ub = nb/den in [0,1]; division kept for the ray
-  // parameter (refinement) and for literal equality with the reference.
   const double ua = na / den, ub = nb / den;
   if (ua_out) *ua_out = ua;
   return !(ua < 0.0 || ua > 1.0 || ub < 0.0 || ub > 1.0);
+}
+
+// ray parameter only (refinement of a hit the search already established)
+__device__ __forceinline__ double ua64(double x1, double y1, double x2, double y2, double x3, double y3, double x4,
+                                       double y4) {
+  const double d43y = ds(y4, y3), d43x = ds(x4, x3), d21x = ds(x2, x1), d21y = ds(y2, y1);
+  const double den = ds(dm(d43y, d21x), dm(d43x, d21y));
+  const double d13y = ds(y1, y3), d13x = ds(x1, x3);
+  const double na = ds(dm(d43x, d13y), dm(d43y, d13x));
+  return na / den;
 }
 
 // boolean-only variant without divisions: sign tests are equivalent to the
@@ -214,9 +250,6 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -224,16 +257,55 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-#define BRS_KEY_NOHIT 0x3F800001u  // just above 1.0f: parameters <= 1 are hits
+// ---- FP32 nearest-hit searches ------------------------------------------------
+// Both keep a key whose integer order is "nearer is better" and the index of
+// the winning segment; ties go to the larger index (the reference keeps the
+// last of equally distant hits).
 
-// FP32 nearest-hit search of one ray against segtab[j0, j1), lane g of SL
-// striding.  key = bits of the ray parameter t (unsigned order == float order
-// for t >= 0; negative / NaN / inf parameters compare above BRS_KEY_NOHIT).
-__device__ __forceinline__ void search32(const float4* __restrict__ segtab, int j0, int j1, int g, int SL, float ox,
-                                         float oy, float rx, float ry, uint32_t& key, int& idx) {
+// Shared-origin form.  tab[j] = (m.x, m.y, q.x, q.y); key = bits of 1/t, larger
+// is nearer, starts at bits(1.0f): only hits with t <= 1 (inside the range)
+// win.  Negative or NaN-free by construction (degenerate entries are zero).
+#define BRS_GKEY_INIT 0x3F800000u
+template <int NR>
+__device__ __forceinline__ void search_group(const float4* __restrict__ tab, int j0, int j1, int g, int SL,
+                                             const float (&rx)[NR], const float (&ry)[NR], uint32_t (&key)[NR],
+                                             int (&idx)[NR]) {
 #pragma unroll 4
   for (int j = j0 + g; j < j1; j += SL) {
-    const float4 s = segtab[j];  // sx, sy, ex, ey
+    const float4 s = tab[j];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const float invt = fmaf(s.x, rx[k], s.y * ry[k]);     // 1/t = m . r
+      const float w = fmaf(rx[k], s.w, -(ry[k] * s.z));     // u/t = r x q
+      // 0 <= w <= invt as one unsigned compare (negative w has the top bit set)
+      if (__float_as_uint(w) <= __float_as_uint(invt) && (int)__float_as_uint(invt) >= (int)key[k]) {
+        key[k] = __float_as_uint(invt);
+        idx[k] = j;
+      }
+    }
+  }
+}
+// reduce over the SL lanes of a group: larger key wins, ties to the larger index
+__device__ __forceinline__ void group_max(uint32_t& key, int& idx, int SL, uint32_t mask) {
+  for (int o = SL >> 1; o > 0; o >>= 1) {
+    const uint32_t k2 = __shfl_xor_sync(mask, key, o);
+    const int i2 = __shfl_xor_sync(mask, idx, o);
+    if ((int)k2 > (int)key || (k2 == key && i2 > idx)) {
+      key = k2;
+      idx = i2;
+    }
+  }
+}
+
+// General form, one ray against segtab[j] = (x1, y1, ex, ey).  key = bits of
+// the ray parameter t (unsigned order == float order for t >= 0; negative / NaN
+// / inf parameters compare above BRS_KEY_NOHIT), smaller is nearer.
+#define BRS_KEY_NOHIT 0x3F800001u  // just above 1.0f: parameters <= 1 are hits
+__device__ __forceinline__ void search_direct(const float4* __restrict__ segtab, int j0, int j1, int g, int SL,
+                                              float ox, float oy, float rx, float ry, uint32_t& key, int& idx) {
+#pragma unroll 4
+  for (int j = j0 + g; j < j1; j += SL) {
+    const float4 s = segtab[j];
     const float dx = ox - s.x, dy = oy - s.y;
     const float den = s.w * rx - s.z * ry;
     const float na = s.z * dy - s.w * dx;
@@ -241,17 +313,12 @@ __device__ __forceinline__ void search32(const float4* __restrict__ segtab, int 
     const float inv = rcp_approx(den);
     const uint32_t tb = __float_as_uint(na * inv);
     const uint32_t ub = __float_as_uint(nb * inv);
-    if (ub <= 0x3F800000u && tb < key) {
+    if (ub <= 0x3F800000u && tb <= key) {
       key = tb;
       idx = j;
     }
   }
 }
-
-// reduce (key, idx) over the SL lanes of a group (SL power of two, groups are
-// aligned lane ranges, `mask` names exactly the group's lanes so that groups of
-// one warp may sit in different branches); ties go to the larger index (the
-// reference keeps the last of equally distant hits)
 __device__ __forceinline__ void group_min(uint32_t& key, int& idx, int SL, uint32_t mask) {
   for (int o = SL >> 1; o > 0; o >>= 1) {
     const uint32_t k2 = __shfl_xor_sync(mask, key, o);
@@ -263,8 +330,8 @@ __device__ __forceinline__ void group_min(uint32_t& key, int& idx, int SL, uint3
   }
 }
 
-// segment j of the current world in float64: static walls from the TMA-landed
-// store (float32 values are exact in float64), robot boxes from dbox.
+// segment j of a world in float64: static walls from the TMA-landed store
+// (float32 values are exact in float64), robot boxes from dbox.
 __device__ __forceinline__ void seg64(const uint32_t* raw, int SC, int S, const double* ws, int j, double& x3,
                                       double& y3, double& x4, double& y4) {
   if (j < S) {
@@ -286,9 +353,9 @@ __device__ __forceinline__ void seg64(const uint32_t* raw, int SC, int S, const 
 // like cast_ray: pos = intersect_hit(...), dist = distance(pos, origin)
 __device__ __forceinline__ double refine64(const uint32_t* raw, int SC, int S, const double* ws, int j, double x1,
                                            double y1, double x2, double y2) {
-  double x3, y3, x4, y4, ua = 0.0;
+  double x3, y3, x4, y4;
   seg64(raw, SC, S, ws, j, x3, y3, x4, y4);
-  isect64(x1, y1, x2, y2, x3, y3, x4, y4, &ua);
+  const double ua = ua64(x1, y1, x2, y2, x3, y3, x4, y4);
   const double px = da(x1, dm(ua, ds(x2, x1))), py = da(y1, dm(ua, ds(y2, y1)));
   const double ex = ds(px, x1), ey = ds(py, y1);
   return sqrt(da(dm(ex, ex), dm(ey, ey)));
@@ -317,9 +384,9 @@ __device__ __forceinline__ void mount_point(const double* wsr, double mx, double
   y1 = da(wsr[BRS_WS_POSE + 1], da(dm(sa, mx), dm(ca, my)));
 }
 
-// Paint rows r0, r0+rstep, ... of the 4 columns of quad q (upstream
-// Camera.take_picture: sky above, shaded wall, ground below, then the strips of
-// other robots back to front).
+// Paint rows r0, r0+rstep, ... of the 4 columns of quad q of one picture
+// (upstream Camera.take_picture: sky above, shaded wall, ground below, then the
+// strips of other robots back to front).
 __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInfo* __restrict__ cinf,
                                            const Strip* __restrict__ strips, int strips_per_col,
                                            const uint32_t* __restrict__ rowsky, const uint32_t* __restrict__ rowgnd,
@@ -359,297 +426,429 @@ __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInf
   }
 }
 
-// PREPARE a world (run by the lanes of one warp): robot state HBM -> shared,
-// heading trig, proposed poses and velocities, committed and proposed box
-// corners (compute_boundingbox), FP32 search table of the static walls.  A
-// robot's proposal depends on nothing but its own state, so all of this is off
-// the collision-test critical path and runs one world ahead.
-__device__ __forceinline__ void prepare_world(const KParams& p, int w, int lane, bool do_move, const uint32_t* raw,
-                                              float4* segtab, double* ws, int* meta) {
-  const int R = p.n_robots, SC = p.seg_cap;
-  const int S = min(p.seg_count[w], SC);
-  if (lane == 0) {
-    meta[0] = S;
-    ((float*)meta)[1] = fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]);
+// Wall column record + robot strips of one camera ray (upstream Camera._update
+// and the per-column part of take_picture).
+__device__ __forceinline__ void camera_column(const KParams& p, const CameraDev& cd, int r, int idx, const uint32_t* raw,
+                                              int SC, int S, const double* ws, double wsize, double x1, double y1,
+                                              double x2, double y2, ColInfo* ci_out, Strip* st) {
+  const int R = p.n_robots;
+  ColInfo ci;
+  ci.rgba = 0; ci.top = -1; ci.bot = -1; ci.n_robot = 0;
+  const double H = (double)cd.height;
+  if (idx >= 0) {
+    const double dist = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2);
+    const double s = clamp01(ds(1.0, dm(dist / wsize, cd.size_fade)));
+    const double sc = clamp01(ds(1.0, dm(dist / wsize, cd.color_fade)));
+    ci.rgba = shade(raw[4 * SC + idx], sc);
+    const double high = dm(ds(1.0, s), H);
+    ci.top = (int)ceil(high / 2.0);
+    ci.bot = (int)ceil(ds(H, high / 2.0));
   }
-  if (lane < R) {
-    const int r = lane;
-    const RobotDev& rd = p.robots[r];
-    double* wsr = ws + r * BRS_WS_STRIDE;
-    const size_t o = ((size_t)w * R + r) * 3;
-    const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
-    const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
-    wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
-    wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
-    double s0, c0;
-    sincos(a, &s0, &c0);
-    wsr[BRS_WS_RCS] = c0;
-    wsr[BRS_WS_RCS + 1] = s0;
-    double px = x, py = y, c1 = c0, s1 = s0;
-    double* pr = wsr + BRS_WS_PROP;
-    if (do_move) {
-      const double* tv = p.tvel + o;
-      const double vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
-      const double vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
-      const double va = deltav(tv[2], v2, rd.va_ramp, p.dt);
-      const double pa = ds(a, dm(va, p.dt));
-      const double ang = da(-pa, BRS_PI_OVER_2);
-      double sn, cs;
-      sincos(ang, &sn, &cs);
-      // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
-      const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
-      const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
-      px = da(x, tvx);
-      py = da(y, tvy);
-      c1 = sn;  // sin(pi/2 - pa) = cos(pa)
-      s1 = cs;  // cos(pi/2 - pa) = sin(pa)
-      pr[8] = px; pr[9] = py; pr[10] = pa;
-      pr[11] = vx; pr[12] = vy; pr[13] = va;
-      pr[14] = c1; pr[15] = s1;
-    }
-    // corner = centre + R(heading) * (corner offset in the a=0 frame)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double ox = rd.cox[k], oy = rd.coy[k];
-      wsr[BRS_WS_DBOX + 2 * k] = da(x, ds(dm(c0, ox), dm(s0, oy)));
-      wsr[BRS_WS_DBOX + 2 * k + 1] = da(y, da(dm(s0, ox), dm(c0, oy)));
-      if (do_move) {
-        pr[2 * k] = da(px, ds(dm(c1, ox), dm(s1, oy)));
-        pr[2 * k + 1] = da(py, da(dm(s1, ox), dm(c1, oy)));
-      }
+  // other robots: every hit is a strip (float64 tests, few segments)
+  for (int o = 0; o < R; ++o) {
+    if (o == r) continue;
+    const RobotDev& od = p.robots[o];
+    for (int e = 0; e < 4; ++e) {
+      double x3, y3, x4, y4, ua;
+      seg64(raw, SC, S, ws, S + 4 * o + e, x3, y3, x4, y4);
+      if (!isect64(x1, y1, x2, y2, x3, y3, x4, y4, &ua)) continue;
+      const double px = da(x1, dm(ua, ds(x2, x1))), py = da(y1, dm(ua, ds(y2, y1)));
+      const double ex = ds(px, x1), ey = ds(py, y1);
+      const double dist = sqrt(da(dm(ex, ex), dm(ey, ey)));
+      const double s = clamp01(ds(1.0, dm(dist / wsize, cd.size_fade)));
+      const double sc = clamp01(ds(1.0, dm(dist / wsize, cd.color_fade)));
+      const int rd_to = (int)rint(dm(H / 2.0, ds(1.0, sc)));
+      const int hgt = (int)rint(dm(dm(od.height, H) / 2.0, s));
+      if (hgt <= 0) continue;
+      Strip sp;
+      sp.rgba = shade(od.rgba, sc);
+      sp.hi = cd.height - 1 - rd_to;
+      sp.lo = cd.height - hgt - rd_to;
+      sp.dist = (float)dist;
+      st[ci.n_robot++] = sp;
     }
   }
-  // derived FP32 search table for the static walls: start point and delta
-  for (int j = lane; j < S; j += 32) {
-    const float x1 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[SC + j]);
-    const float x2 = __uint_as_float(raw[2 * SC + j]), y2 = __uint_as_float(raw[3 * SC + j]);
-    segtab[j] = make_float4(x1, y1, x2 - x1, y2 - y1);
-  }
-  __syncwarp();
-  if (!do_move && lane < 4 * R) {  // nobody moves: the boxes above are final
-    const int r = lane >> 2, e = lane & 3, e2 = (e + 1) & 3;
-    const double* box = ws + r * BRS_WS_STRIDE + BRS_WS_DBOX;
-    const float x1 = (float)box[2 * e], y1 = (float)box[2 * e + 1];
-    const float x2 = (float)box[2 * e2], y2 = (float)box[2 * e2 + 1];
-    segtab[S + lane] = make_float4(x1, y1, x2 - x1, y2 - y1);
-  }
+  *ci_out = ci;
 }
 
 // ------------------------------------------------------------------------------
-// The fused World.step kernel
+// The fused World.step kernel.  NR = camera columns per thread.
 // ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(320, 3) brs_step_kernel(const __grid_constant__ KParams p) {
+template <int NR>
+__global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
-  const int R = p.n_robots, SC = p.seg_cap;
-  const SmemLayout L = make_layout(SC, R, p.n_camera, p.cam_w, p.cam_h);
-  uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
+  const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
+  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h);
+  float4* const segtab = (float4*)(smem + L.segtab);
+  float4* const gtab = (float4*)(smem + L.gtab);
+  double* const wsb = (double*)(smem + L.ws);
+  double2* const org = (double2*)(smem + L.org);
+  int4* const cflag = (int4*)(smem + L.cflag);
+  int2* const meta = (int2*)(smem + L.meta);
   ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
   Strip* const strips = (Strip*)(smem + L.strips);
   double2* const camcs = (double2*)(smem + L.camcs);
   uint32_t* const rowsky = (uint32_t*)(smem + L.rowsky);
   uint32_t* const rowgnd = (uint32_t*)(smem + L.rowgnd);
+  uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
+  volatile int* const sched = (volatile int*)(smem + L.sched);
   const int strips_per_col = 4 * (R - 1);
-  const uint32_t rec_bytes = (uint32_t)(5 * SC * 4);
+  const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
   const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
-  const bool is_helper = (tid >= p.TA) && (tid < p.TA + 32);  // first warp of pool B
-  const int G = gridDim.x;
 
-  // ---- prologue: barriers, TMA for the first two worlds, camera tables, PREPARE world 0
+  // ---- prologue: barriers, first two tiles, camera tables ----------------------
   if (tid == 0) {
     mbar_init(smem_u32(&mbar[0]), 1);
     mbar_init(smem_u32(&mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int b = 0; b < 2; ++b) {
-      const int wb = blockIdx.x + b * G;
-      if (wb < p.n_worlds) {
-        mbar_expect_tx(smem_u32(&mbar[b]), rec_bytes);
-        tma_bulk_g2s(smem_u32(smem + L.raw[b]), p.seg + (size_t)wb * 5 * SC, rec_bytes, smem_u32(&mbar[b]));
-      }
+    const int t0 = (int)atomicAdd(&p.sched[0], 1u);
+    sched[0] = t0;
+    if (t0 < p.n_tiles) {
+      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
+      mbar_expect_tx(smem_u32(&mbar[0]), nw * world_bytes);
+      tma_bulk_g2s(smem_u32(smem + L.raw[0]), p.seg + (size_t)w0 * 5 * SC, nw * world_bytes, smem_u32(&mbar[0]));
     }
   }
-  for (int i = tid; i < p.n_camera * p.cam_w; i += T) camcs[i] = p.cam_cs[i];
-  for (int i = tid; i < p.cam_h; i += T) {
+  for (int i = tid; i < p.n_camera * p.cam_w; i += NT) camcs[i] = p.cam_cs[i];
+  for (int i = tid; i < p.cam_h; i += NT) {
     rowsky[i] = p.row_sky[i];
     rowgnd[i] = p.row_gnd[i];
   }
   __syncthreads();
-  if (is_helper && (int)blockIdx.x < p.n_worlds) {
-    mbar_wait(smem_u32(&mbar[0]), 0);
-    prepare_world(p, blockIdx.x, lane, do_move, (const uint32_t*)(smem + L.raw[0]), (float4*)(smem + L.segtab[0]),
-                  (double*)(smem + L.ws[0]), (int*)(smem + L.meta[0]));
-  }
-  __syncthreads();
 
   int it = 0;
-  for (int w = blockIdx.x; w < p.n_worlds; w += G, ++it) {
+  for (int tile = sched[0]; tile < p.n_tiles; ++it) {
     const int buf = it & 1;
-    const uint32_t* raw = (const uint32_t*)(smem + L.raw[buf]);
-    float4* const segtab = (float4*)(smem + L.segtab[buf]);
-    double* const ws = (double*)(smem + L.ws[buf]);
-    const int S = ((const int*)(smem + L.meta[buf]))[0];
-    const double wsize = (double)((const float*)(smem + L.meta[buf]))[1];
-    // the wall store of this world landed long ago (the helper waited on it);
-    // every thread still observes the barrier phase itself before reading TMA data
-    mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
-    // TMA for world it+1 into the other buffer (free since the end of iteration it-1);
-    // iteration 0's was issued in the prologue
-    if (tid == 0 && it >= 1) {
-      const int wn = w + G;
-      if (wn < p.n_worlds) {
-        mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), rec_bytes);
-        tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, rec_bytes,
+    const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
+    const uint32_t* const rawb = (const uint32_t*)(smem + L.raw[buf]);
+    // fetch the next tile index and start its TMA into the other buffer (free
+    // since the barrier that ended the previous iteration)
+    if (tid == 0) {
+      const int tn = (int)atomicAdd(&p.sched[0], 1u);
+      sched[1 + (buf ^ 1)] = tn;
+      if (tn < p.n_tiles) {
+        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
+        mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
+        tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
                      smem_u32(&mbar[buf ^ 1]));
       }
     }
 
-    // ---------------- phase 1: collision tests in list order ---------------------
-    // robot i sees the already-moved boxes of the robots before it.  FP64,
-    // decisions equal the float64 reference's.
-    if (do_move) {
-      for (int i = 0; i < R; ++i) {
-        double* wsi = ws + i * BRS_WS_STRIDE;
-        const double* pr = wsi + BRS_WS_PROP;
-        int hit = 0;
-        {
-          double ex1[4], ey1[4], edx[4], edy[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int e2 = (e + 1) & 3;
-            ex1[e] = pr[2 * e];
-            ey1[e] = pr[2 * e + 1];
-            edx[e] = ds(pr[2 * e2], pr[2 * e]);
-            edy[e] = ds(pr[2 * e2 + 1], pr[2 * e + 1]);
-          }
-          const int nseg = S + 4 * R;
-          for (int j = tid; j < nseg; j += T) {
-            if (j >= S && ((j - S) >> 2) == i) continue;  // never collide with yourself
-            double x3, y3, x4, y4;
-            seg64(raw, SC, S, ws, j, x3, y3, x4, y4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) hit |= (int)isect64_bool(ex1[e], ey1[e], edx[e], edy[e], x3, y3, x4, y4);
-          }
-        }
-        hit = __syncthreads_or(hit);
-        // commit or stall; everything below reads stable sources (old box or proposal)
-        if (tid < 4) {  // this robot's box as FP32 search segments for the sensors
-          const int e = tid, e2 = (e + 1) & 3;
-          const double* src = hit ? wsi + BRS_WS_DBOX : pr;
-          const float x1 = (float)src[2 * e], y1 = (float)src[2 * e + 1];
-          const float x2 = (float)src[2 * e2], y2 = (float)src[2 * e2 + 1];
-          segtab[S + 4 * i + e] = make_float4(x1, y1, x2 - x1, y2 - y1);
-        }
-        if (tid < 3) {
-          const size_t o = ((size_t)w * R + i) * 3 + tid;
-          if (!hit) {
-            p.pose[o] = pr[8 + tid];
-            p.vel[o] = pr[11 + tid];
-          } else {
-            p.vel[o] = 0.0;
-          }
-        }
-        if (tid == 0) p.stalled[(size_t)w * R + i] = (uint8_t)(hit ? 1 : 0);
-        // (__syncthreads_or was a barrier: nobody is still testing against the old box)
-        if (!hit) {
-          if (tid < 8) wsi[BRS_WS_DBOX + tid] = pr[tid];
-          if (tid < 3) wsi[BRS_WS_POSE + tid] = pr[8 + tid];
-          if (tid == 8) { wsi[BRS_WS_RCS] = pr[14]; wsi[BRS_WS_RCS + 1] = pr[15]; }
-        }
-        __syncthreads();  // robot i+1's tests and the sensors read the boxes / poses
+    // ---------------- phase 1: PREP ------------------------------------------------
+    // thread per (world, robot): state HBM -> shared, heading trig, proposed pose and
+    // velocity, committed and proposed box corners (compute_boundingbox)
+    for (int i = tid; i < nw * R; i += NT) {
+      const int wl = i / R, r = i - wl * R, w = w0 + wl;
+      const RobotDev& rd = p.robots[r];
+      double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
+      const size_t o = ((size_t)w * R + r) * 3;
+      const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
+      const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
+      wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
+      wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
+      double s0, c0;
+      sincos(a, &s0, &c0);
+      wsr[BRS_WS_RCS] = c0;
+      wsr[BRS_WS_RCS + 1] = s0;
+      double px = x, py = y, c1 = c0, s1 = s0;
+      double* pr = wsr + BRS_WS_PROP;
+      if (do_move) {
+        const double* tv = p.tvel + o;
+        const double vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
+        const double vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
+        const double va = deltav(tv[2], v2, rd.va_ramp, p.dt);
+        const double pa = ds(a, dm(va, p.dt));
+        const double ang = da(-pa, BRS_PI_OVER_2);
+        double sn, cs;
+        sincos(ang, &sn, &cs);
+        // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
+        const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
+        const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
+        px = da(x, tvx);
+        py = da(y, tvy);
+        c1 = sn;  // sin(pi/2 - pa) = cos(pa)
+        s1 = cs;  // cos(pi/2 - pa) = sin(pa)
+        pr[8] = px; pr[9] = py; pr[10] = pa;
+        pr[11] = vx; pr[12] = vy; pr[13] = va;
+        pr[14] = c1; pr[15] = s1;
       }
+      // corner = centre + R(heading) * (corner offset in the a=0 frame)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double ox = rd.cox[k], oy = rd.coy[k];
+        wsr[BRS_WS_DBOX + 2 * k] = da(x, ds(dm(c0, ox), dm(s0, oy)));
+        wsr[BRS_WS_DBOX + 2 * k + 1] = da(y, da(dm(s0, ox), dm(c0, oy)));
+        if (do_move) {
+          pr[2 * k] = da(px, ds(dm(c1, ox), dm(s1, oy)));
+          pr[2 * k + 1] = da(py, da(dm(s1, ox), dm(c1, oy)));
+        }
+      }
+      cflag[i] = make_int4(0, 0, 0, 0);
     }
+    for (int wl = tid; wl < nw; wl += NT) {
+      const int w = w0 + wl;
+      meta[wl].x = min(max(p.seg_count[w], 0), SC);
+      meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
+    }
+    // the wall store of this tile has landed (every thread observes the phase itself)
+    mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+    // FP32 segment table of the static walls: start point and delta
+    for (int i = tid; i < nw * SC; i += NT) {
+      const int wl = i / SC, j = i - wl * SC;
+      const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+      const float x1 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[SC + j]);
+      const float x2 = __uint_as_float(raw[2 * SC + j]), y2 = __uint_as_float(raw[3 * SC + j]);
+      segtab[(size_t)wl * nvis + j] = make_float4(x1, y1, x2 - x1, y2 - y1);
+    }
+    __syncthreads();
 
-    // ---------------- phase 2: ray-cast sensors (+ PREPARE of the next world) -----
-    if (tid < p.TA) {
-      // ---- pool A: one camera column per thread (upstream Camera._update + the
-      //      per-column part of take_picture), then the pictures
-      if (do_cam) {
-        const int ncols = p.n_camera * p.cam_w;
-        for (int col = tid; col < ncols; col += p.TA) {
-          const int c = col / p.cam_w;
-          const CameraDev& cd = p.cameras[c];
-          const int r = cd.robot;
-          double x1, y1, ca, sa;
-          mount_point(ws + r * BRS_WS_STRIDE, cd.mx, cd.my, x1, y1, ca, sa);
-          const double2 cs = camcs[col];
-          const double dxu = ds(dm(ca, cs.x), dm(sa, cs.y));  // cos(a + theta_i)
-          const double dyu = da(dm(sa, cs.x), dm(ca, cs.y));  // sin(a + theta_i)
-          const double x2 = da(dm(dxu, cd.max_range), x1), y2 = da(dm(dyu, cd.max_range), y1);
-          const float ox = (float)x1, oy = (float)y1;
-          const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
-          uint32_t key = BRS_KEY_NOHIT;
-          int idx = -1;
-          search32(segtab, 0, S, 0, 1, ox, oy, rx, ry, key, idx);  // walls only (height == 1)
-          ColInfo ci;
-          ci.rgba = 0; ci.top = -1; ci.bot = -1; ci.n_robot = 0;
-          const double H = (double)cd.height;
-          if (idx >= 0) {
-            const double dist = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2);
-            const double s = clamp01(ds(1.0, dm(dist / wsize, cd.size_fade)));
-            const double sc = clamp01(ds(1.0, dm(dist / wsize, cd.color_fade)));
-            ci.rgba = shade(raw[4 * SC + idx], sc);
-            const double high = dm(ds(1.0, s), H);
-            ci.top = (int)ceil(high / 2.0);
-            ci.bot = (int)ceil(ds(H, high / 2.0));
-          }
-          // other robots: every hit is a strip (float64 tests, few segments)
-          Strip* st = strips + (size_t)col * strips_per_col;
-          for (int o = 0; o < R; ++o) {
-            if (o == r) continue;
-            const RobotDev& od = p.robots[o];
-            for (int e = 0; e < 4; ++e) {
-              double x3, y3, x4, y4, ua;
-              seg64(raw, SC, S, ws, S + 4 * o + e, x3, y3, x4, y4);
-              if (!isect64(x1, y1, x2, y2, x3, y3, x4, y4, &ua)) continue;
-              const double px = da(x1, dm(ua, ds(x2, x1))), py = da(y1, dm(ua, ds(y2, y1)));
-              const double ex = ds(px, x1), ey = ds(py, y1);
-              const double dist = sqrt(da(dm(ex, ex), dm(ey, ey)));
-              const double s = clamp01(ds(1.0, dm(dist / wsize, cd.size_fade)));
-              const double sc = clamp01(ds(1.0, dm(dist / wsize, cd.color_fade)));
-              const int rd_to = (int)rint(dm(H / 2.0, ds(1.0, sc)));
-              const int hgt = (int)rint(dm(dm(od.height, H) / 2.0, s));
-              if (hgt <= 0) continue;
-              Strip sp;
-              sp.rgba = shade(od.rgba, sc);
-              sp.hi = cd.height - 1 - rd_to;
-              sp.lo = cd.height - hgt - rd_to;
-              sp.dist = (float)dist;
-              st[ci.n_robot++] = sp;
+    if (do_move) {
+      // ---------------- phase 2: COLLIDE ---------------------------------------------
+      // walls: GS threads per (world, robot) stride over its segments.  FP32 disc cull
+      // (distance of the proposed centre to the segment vs the box circumradius plus a
+      // margin far above FP32 error), then the exact FP64 4-edge test.
+      {
+        const int GS = p.GS, gi = tid / GS, gl = tid - gi * GS, ngrp = NT / GS;
+        for (int i = gi; i < nw * R; i += ngrp) {
+          const int wl = i / R, r = i - wl * R;
+          const int S = meta[wl].x;
+          const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
+          const float cx = (float)pr[8], cy = (float)pr[9];
+          const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
+          const float rad2 = rad * rad;
+          const float4* st = segtab + (size_t)wl * nvis;
+          bool hit = false;
+          for (int j = gl; j < S; j += GS) {
+            const float4 s = st[j];
+            const float ax = cx - s.x, ay = cy - s.y;
+            const float ee = fmaf(s.z, s.z, s.w * s.w);
+            float h = fmaf(ax, s.z, ay * s.w) * rcp_approx(ee);
+            h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
+            const float vx = fmaf(-h, s.z, ax), vy = fmaf(-h, s.w, ay);
+            if (fmaf(vx, vx, vy * vy) <= rad2) {
+              const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+              const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
+              const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int e2 = (e + 1) & 3;
+                hit |= isect64_bool(pr[2 * e], pr[2 * e + 1], ds(pr[2 * e2], pr[2 * e]),
+                                    ds(pr[2 * e2 + 1], pr[2 * e + 1]), x3, y3, x4, y4);
+              }
             }
           }
-          colinfo[col] = ci;
+          if (hit) cflag[i].x = 1;
         }
-        // ---------------- phase 3: Camera.take_picture (pool A only) ---------------
-        named_bar_sync(1, p.TA);
-        const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
-        for (int c = 0; c < p.n_camera; ++c) {
-          uint4* out = (uint4*)(p.cam_out + ((size_t)w * p.n_camera + c) * (size_t)H * W * 4);
-          const ColInfo* cinf = colinfo + c * W;
-          const Strip* cst = strips + (size_t)c * W * strips_per_col;
-          // thread -> (column quad q, rows r0, r0+rstep, ...): the 4 column records stay
-          // in registers, a warp writes 512 contiguous bytes per store instruction
-          const int rstep = p.TA / Q;
-          if (rstep > 0) {
-            const int q = tid % Q, r0 = tid / Q;
-            if (r0 < rstep) paint_rows(out, cinf, cst, strips_per_col, rowsky, rowgnd, q, Q, r0, rstep, H);
+      }
+      // robots: proposal i against the committed box of o (pair_old) and, for o < i,
+      // against the proposal of o (pair_new): Robot.step's list order becomes masks
+      if (R > 1) {
+        const int per_world = R * R * 2;
+        for (int i = tid; i < nw * per_world; i += NT) {
+          const int wl = i / per_world, k = i - wl * per_world;
+          const int ri = k / (2 * R), ro = (k >> 1) % R, v = k & 1;
+          if (ro == ri || (v && ro > ri)) continue;
+          const double* wi = wsb + (size_t)(wl * R + ri) * BRS_WS_STRIDE;
+          const double* wo = wsb + (size_t)(wl * R + ro) * BRS_WS_STRIDE;
+          const double* pr = wi + BRS_WS_PROP;
+          const double* ob = v ? wo + BRS_WS_PROP : wo + BRS_WS_DBOX;
+          const double ocx = v ? wo[BRS_WS_PROP + 8] : wo[BRS_WS_POSE], ocy = v ? wo[BRS_WS_PROP + 9] : wo[BRS_WS_POSE + 1];
+          const double ddx = pr[8] - ocx, ddy = pr[9] - ocy;
+          const double reach = p.robots[ri].radius + p.robots[ro].radius + (double)p.cull_margin;
+          if (ddx * ddx + ddy * ddy > reach * reach) continue;
+          bool hit = false;
+          for (int e = 0; e < 4; ++e) {
+            const int e2 = (e + 1) & 3;
+            const double x1 = pr[2 * e], y1 = pr[2 * e + 1];
+            const double ex = ds(pr[2 * e2], x1), ey = ds(pr[2 * e2 + 1], y1);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              const int f2 = (f + 1) & 3;
+              hit |= isect64_bool(x1, y1, ex, ey, ob[2 * f], ob[2 * f + 1], ob[2 * f2], ob[2 * f2 + 1]);
+            }
+          }
+          if (hit) atomicOr(v ? &cflag[wl * R + ri].z : &cflag[wl * R + ri].y, 1 << ro);
+        }
+      }
+      __syncthreads();
+
+      // ---------------- phase 3: COMMIT ----------------------------------------------
+      // thread per (world, robot): replay the list order on the masks, commit or stall
+      for (int i = tid; i < nw * R; i += NT) {
+        const int wl = i / R, r = i - wl * R, w = w0 + wl;
+        unsigned stalled_mask = 0;
+        bool hit = false;
+        for (int q = 0; q <= r; ++q) {
+          const int4 f = cflag[wl * R + q];
+          // robots before q: their proposal if they moved, their old box if they stalled;
+          // robots after q have not moved yet
+          const unsigned before = (1u << q) - 1u;
+          const unsigned m = ((unsigned)f.z & before & ~stalled_mask) | ((unsigned)f.y & (~before | stalled_mask));
+          hit = f.x || m;
+          if (hit) stalled_mask |= 1u << q;
+        }
+        double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
+        const double* pr = wsr + BRS_WS_PROP;
+        const size_t o = ((size_t)w * R + r) * 3;
+        if (!hit) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            p.pose[o + k] = pr[8 + k];
+            p.vel[o + k] = pr[11 + k];
+            wsr[BRS_WS_POSE + k] = pr[8 + k];
+          }
+          wsr[BRS_WS_RCS] = pr[14];
+          wsr[BRS_WS_RCS + 1] = pr[15];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) p.vel[o + k] = 0.0;
+        }
+        p.stalled[(size_t)w * R + r] = (uint8_t)(hit ? 1 : 0);
+        cflag[i].w = hit ? 1 : 0;
+      }
+      __syncthreads();
+      // moved robots take their proposed box (nobody reads DBOX as "old" any more)
+      for (int i = tid; i < nw * R * 8; i += NT) {
+        const int ir = i >> 3, k = i & 7;
+        if (!cflag[ir].w) wsb[(size_t)ir * BRS_WS_STRIDE + BRS_WS_DBOX + k] = wsb[(size_t)ir * BRS_WS_STRIDE + BRS_WS_PROP + k];
+      }
+      __syncthreads();
+    }
+
+    if (do_sense || do_cam) {
+      // robot boxes as FP32 search segments; origins of the ray groups
+      for (int i = tid; i < nw * R * 4; i += NT) {
+        const int ir = i >> 2, e = i & 3, e2 = (e + 1) & 3, wl = ir / R, r = ir - wl * R;
+        const double* box = wsb + (size_t)ir * BRS_WS_STRIDE + BRS_WS_DBOX;
+        const float x1 = (float)box[2 * e], y1 = (float)box[2 * e + 1];
+        const float x2 = (float)box[2 * e2], y2 = (float)box[2 * e2 + 1];
+        segtab[(size_t)wl * nvis + meta[wl].x + 4 * r + e] = make_float4(x1, y1, x2 - x1, y2 - y1);
+      }
+      for (int i = tid; i < nw * NG; i += NT) {
+        const int wl = i / NG, g = i - wl * NG;
+        const GroupDev& gd = p.groups[g];
+        double x1, y1, ca, sa;
+        mount_point(wsb + (size_t)(wl * R + gd.robot) * BRS_WS_STRIDE, gd.mx, gd.my, x1, y1, ca, sa);
+        org[i] = make_double2(x1, y1);
+      }
+      __syncthreads();
+
+      // ---------------- phase 4: TABLE -------------------------------------------------
+      // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,
+      // na = ex*dy - ey*dx.  The own robot's edges and degenerate entries are zero (no hit).
+      if (NG > 0) {
+        const int per_world = NG * nvis;
+        for (int i = tid; i < nw * per_world; i += NT) {
+          const int wl = i / per_world, k = i - wl * per_world;
+          const int g = k / nvis, j = k - g * nvis;
+          const int S = meta[wl].x, nv = S + 4 * R;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < nv && !(j >= S && ((j - S) >> 2) == p.groups[g].robot)) {
+            const float4 s = segtab[(size_t)wl * nvis + j];
+            const double2 O = org[wl * NG + g];
+            const float dx = (float)(O.x - (double)s.x), dy = (float)(O.y - (double)s.y);
+            const float na = fmaf(s.z, dy, -(s.w * dx));
+            if (fabsf(na) > 1e-30f) {
+              const float inv = 1.0f / na;
+              t = make_float4(s.w * inv, -s.z * inv, dx * inv, dy * inv);
+            }
+          }
+          gtab[(size_t)wl * per_world + k] = t;
+        }
+        __syncthreads();
+      }
+
+      // ---------------- phase 5: SENSE ---------------------------------------------------
+      // 5a. group path: camera column blocks, then grouped range sensors
+      {
+        const int SL = p.SLG, g = tid & (SL - 1), slot = tid / SL, nslot = NT / SL;
+        const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
+        const int cblocks = do_cam ? p.n_camera * (p.cam_w / NR) : 0;
+        const int ngr = do_sense ? p.n_gr : 0;
+        const int ntask = cblocks + ngr;
+        for (int i = slot; i < nw * ntask; i += nslot) {
+          const int wl = i / ntask, task = i - wl * ntask, w = w0 + wl;
+          const int S = meta[wl].x;
+          const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+          if (task < cblocks) {
+            const int cpb = p.cam_w / NR;  // column blocks per camera
+            const int c = task / cpb, col0 = (task - c * cpb) * NR;
+            const CameraDev& cd = p.cameras[c];
+            const int r = cd.robot;
+            const double2 O = org[wl * NG + cd.group];
+            const double ca = ws[r * BRS_WS_STRIDE + BRS_WS_RCS], sa = ws[r * BRS_WS_STRIDE + BRS_WS_RCS + 1];
+            double x2[NR], y2[NR];
+            float rx[NR], ry[NR];
+            uint32_t key[NR];
+            int idx[NR];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+              const double2 cs = camcs[c * p.cam_w + col0 + k];
+              const double dxu = ds(dm(ca, cs.x), dm(sa, cs.y));  // cos(a + theta_i)
+              const double dyu = da(dm(sa, cs.x), dm(ca, cs.y));  // sin(a + theta_i)
+              x2[k] = da(dm(dxu, cd.max_range), O.x);
+              y2[k] = da(dm(dyu, cd.max_range), O.y);
+              rx[k] = (float)ds(x2[k], O.x);
+              ry[k] = (float)ds(y2[k], O.y);
+              key[k] = BRS_GKEY_INIT;
+              idx[k] = -1;
+            }
+            // walls only (height == 1); other robots become strips below
+            search_group<NR>(gtab + ((size_t)wl * NG + cd.group) * nvis, 0, S, g, SL, rx, ry, key, idx);
+            const double wsize = (double)__int_as_float(meta[wl].y);
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+              if (SL > 1) group_max(key[k], idx[k], SL, gmask);
+              if (g == 0) {
+                const size_t col = ((size_t)wl * p.n_camera + c) * p.cam_w + col0 + k;
+                camera_column(p, cd, r, idx[k], raw, SC, S, ws, wsize, O.x, O.y, x2[k], y2[k], colinfo + col,
+                              strips + col * strips_per_col);
+              }
+            }
           } else {
-            // image wider than 4 x threads: several quads per thread
-            for (int q = tid; q < Q; q += p.TA) paint_rows(out, cinf, cst, strips_per_col, rowsky, rowgnd, q, Q, 0, 1, H);
+            // RangeSensor.update on a shared-origin mount
+            const int si = p.gr_idx[task - cblocks];
+            const RangeDev& sd = p.ranges[si];
+            const int r = sd.robot;
+            const double2 O = org[wl * NG + sd.group];
+            const double ca = ws[r * BRS_WS_STRIDE + BRS_WS_RCS], sa = ws[r * BRS_WS_STRIDE + BRS_WS_RCS + 1];
+            double reading = 1.0;
+            for (int k = 0; k < sd.n_rays; ++k) {
+              const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
+              const double dyu = da(dm(sa, sd.cr[k]), dm(ca, sd.sr[k]));
+              const double x2 = da(dm(dxu, sd.max), O.x), y2 = da(dm(dyu, sd.max), O.y);
+              float rx[1] = {(float)ds(x2, O.x)}, ry[1] = {(float)ds(y2, O.y)};
+              uint32_t key[1] = {BRS_GKEY_INIT};
+              int idx[1] = {-1};
+              search_group<1>(gtab + ((size_t)wl * NG + sd.group) * nvis, 0, S + 4 * R, g, SL, rx, ry, key, idx);
+              if (SL > 1) group_max(key[0], idx[0], SL, gmask);
+              if (g == 0 && idx[0] >= 0) {
+                const double d = refine64(raw, SC, S, ws, idx[0], O.x, O.y, x2, y2);
+                if (d < dm(reading, sd.max)) reading = d / sd.max;
+              }
+            }
+            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)dm(reading, sd.max);
           }
         }
       }
-    } else if (tid < p.TA + p.TB) {
-      // ---- pool B: range / light / smell sensors, SL lanes per ray
+      // 5b. direct path: range sensors on their own mount, light and smell sensors
       if (do_sense) {
-        const int l = tid - p.TA, SL = p.SL;
-        const int g = l & (SL - 1), grp = l / SL, ngrp = p.TB / SL;
+        const int SL = p.SLD, g = tid & (SL - 1), slot = tid / SL, nslot = NT / SL;
         const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
-        const int ntask = p.n_range + p.n_light + p.n_smell;
-        const int nseg = S + 4 * R;
-        for (int task = grp; task < ntask; task += ngrp) {  // task is uniform over a lane group
-          if (task < p.n_range) {
+        const int ntask = p.n_dr + p.n_light + p.n_smell;
+        for (int i = slot; i < nw * ntask; i += nslot) {
+          const int wl = i / ntask, task = i - wl * ntask, w = w0 + wl;
+          const int S = meta[wl].x, nseg = S + 4 * R;
+          const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+          const float4* st = segtab + (size_t)wl * nvis;
+          if (task < p.n_dr) {
             // RangeSensor.update
-            const RangeDev& sd = p.ranges[task];
+            const int si = p.dr_idx[task];
+            const RangeDev& sd = p.ranges[si];
             const int r = sd.robot;
             double x1, y1, ca, sa;
             mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
@@ -663,18 +862,18 @@ __global__ void __launch_bounds__(320, 3) brs_step_kernel(const __grid_constant_
               const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
               uint32_t key = BRS_KEY_NOHIT;
               int idx = -1;
-              search32(segtab, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-              search32(segtab, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-              group_min(key, idx, SL, gmask);
+              search_direct(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+              search_direct(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+              if (SL > 1) group_min(key, idx, SL, gmask);
               if (g == 0 && idx >= 0) {
                 const double d = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2);
                 if (d < dm(reading, sd.max)) reading = d / sd.max;
               }
             }
-            if (g == 0) p.range_out[(size_t)w * p.n_range + task] = (float)dm(reading, sd.max);
-          } else if (task < p.n_range + p.n_light) {
+            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)dm(reading, sd.max);
+          } else if (task < p.n_dr + p.n_light) {
             // LightSensor.update: line of sight to every bulb
-            const int li = task - p.n_range;
+            const int li = task - p.n_dr;
             const PointDev& sd = p.lights[li];
             const int r = sd.robot;
             double x1, y1, ca, sa;
@@ -690,15 +889,15 @@ __global__ void __launch_bounds__(320, 3) brs_step_kernel(const __grid_constant_
               const float rx = (float)ex, ry = (float)ey;
               uint32_t key = BRS_KEY_NOHIT;
               int idx = -1;
-              search32(segtab, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-              search32(segtab, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-              group_min(key, idx, SL, gmask);
+              search_direct(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+              search_direct(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+              if (SL > 1) group_min(key, idx, SL, gmask);
               if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
             }
             if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
           } else {
             // SmellSensor.update: grid lookup at the mount point
-            const int si = task - p.n_range - p.n_light;
+            const int si = task - p.n_dr - p.n_light;
             const PointDev& sd = p.smells[si];
             const int r = sd.robot;
             double x1, y1, ca, sa;
@@ -713,19 +912,45 @@ __global__ void __launch_bounds__(320, 3) brs_step_kernel(const __grid_constant_
           }
         }
       }
-      // ---- helper warp: PREPARE the next world while pool A is still busy
-      if (is_helper) {
-        __syncwarp();
-        const int wn = w + G;
-        if (wn < p.n_worlds) {
-          const int nb = buf ^ 1;
-          mbar_wait(smem_u32(&mbar[nb]), (uint32_t)((it + 1) >> 1) & 1u);
-          prepare_world(p, wn, lane, do_move, (const uint32_t*)(smem + L.raw[nb]), (float4*)(smem + L.segtab[nb]),
-                        (double*)(smem + L.ws[nb]), (int*)(smem + L.meta[nb]));
+
+      // ---------------- phase 6: PAINT ---------------------------------------------------
+      if (do_cam) {
+        __syncthreads();
+        const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
+        const int nimg = nw * p.n_camera;
+        uint4* const out0 = (uint4*)(p.cam_out + (size_t)w0 * p.n_camera * (size_t)H * W * 4);
+        if (NT >= Q) {
+          // thread -> (picture slot, row slot, column quad): the 4 column records stay in
+          // registers over the rows, a warp writes whole 128-byte lines per store
+          const int q = tid % Q, rest = tid / Q, RS = p.paint_rs;
+          const int rslot = rest % RS, islot = rest / RS, nislot = (NT / Q) / RS;
+          if (islot < nislot) {
+            for (int im = islot; im < nimg; im += nislot)
+              paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
+                         strips_per_col, rowsky, rowgnd, q, Q, rslot, RS, H);
+          }
+        } else {
+          // picture wider than 4 x threads: several quads per thread
+          for (int im = 0; im < nimg; ++im)
+            for (int q = tid; q < Q; q += NT)
+              paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
+                         strips_per_col, rowsky, rowgnd, q, Q, 0, 1, H);
         }
       }
     }
-    __syncthreads();  // world w is done; world w+1 is prepared
+    __syncthreads();  // tile done: its buffers are free, the next tile index is visible
+    tile = sched[1 + (buf ^ 1)];
+  }
+
+  // self-resetting scheduler: the last CTA to leave zeroes both counters for the next launch
+  if (tid == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(&p.sched[1], 1u);
+    if (done == gridDim.x - 1) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
