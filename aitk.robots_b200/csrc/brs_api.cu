@@ -54,7 +54,8 @@ struct brs_engine {
   unsigned int* d_sched = nullptr;
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
-  int T = 256, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
+  int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
+  int gtasks = 0, dtasks = 0;
 };
 
 static int pow2floor(int x) {
@@ -248,7 +249,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     int k = find_group(robot, mx, my);
     if (k < 0) {
       GroupDev g;
-      g.robot = robot; g._pad = 0; g.mx = mx; g.my = my;
+      memset(&g, 0, sizeof(g));
+      g.robot = robot; g.mx = mx; g.my = my;
       groups.push_back(g);
       k = (int)groups.size() - 1;
     }
@@ -266,6 +268,49 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
         if (rays >= group_min) k = add_group(g.robot, g.mx, g.my);
       }
       g.group = k;
+    }
+  }
+  // what each group's rays can reach: longest range and the cone of directions (robot frame)
+  {
+    const double PI = 3.14159265358979323846;
+    for (size_t k = 0; k < groups.size(); ++k) {
+      std::vector<double> ang;
+      double range = 0;
+      for (int i = 0; i < cfg->n_camera; ++i)
+        if (cdev[i].group == (int)k) {
+          const brs_camera_desc& d = e->cameras[i];
+          ang.push_back(-d.fov / 2);
+          ang.push_back((double)(d.width - 1) / (double)d.width * d.fov - d.fov / 2);
+          range = std::fmax(range, d.max_range);
+        }
+      for (int i = 0; i < cfg->n_range; ++i)
+        if (gdev[i].group == (int)k) {
+          for (int q = 0; q < gdev[i].n_rays; ++q) ang.push_back(std::atan2(gdev[i].sr[q], gdev[i].cr[q]));
+          range = std::fmax(range, gdev[i].max);
+        }
+      GroupDev& g = groups[k];
+      g.range = (float)(range * (1.0 + 1e-4) + 1e-3);
+      g.has_cone = 0;
+      // smallest arc containing all directions: try every direction as the arc's start
+      double best_w = 1e9, best_lo = 0;
+      for (double a0 : ang) {
+        double w = 0;
+        for (double a : ang) {
+          double d = std::fmod(a - a0, 2 * PI);
+          if (d < 0) d += 2 * PI;
+          w = std::fmax(w, d);
+        }
+        if (w < best_w) { best_w = w; best_lo = a0; }
+      }
+      const double margin = 2e-3;
+      if (!ang.empty() && best_w + 2 * margin < PI - 0.02 && !env_int("BRS_NO_CONE", 0)) {
+        const double lo = best_lo - margin, hi = best_lo + best_w + margin, ax = 0.5 * (lo + hi);
+        g.has_cone = 1;
+        g.lo_c = (float)std::cos(lo); g.lo_s = (float)std::sin(lo);
+        g.hi_c = (float)std::cos(hi); g.hi_s = (float)std::sin(hi);
+        g.ax_c = (float)std::cos(ax); g.ax_s = (float)std::sin(ax);
+      }
+      if (env_int("BRS_NO_RANGE_CULL", 0)) g.range = 3.0e18f;
     }
   }
   std::vector<int> gr_idx, dr_idx;
@@ -335,16 +380,27 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   if (e->cam_w % std::max(e->NR, 1)) e->NR = 1;
   const int gtasks = ncols / e->NR + e->n_gr;
   const int dtasks = e->n_dr + cfg->n_light + cfg->n_smell;
+  e->gtasks = gtasks;
+  e->dtasks = dtasks;
   const int tasks = std::max(gtasks + dtasks, 1);
-  e->T = env_int("BRS_NT", 256);
-  if (e->T != 64 && e->T != 128 && e->T != 256) e->T = 256;
+  e->NW = env_int("BRS_NW", 256);
+  if (e->NW != 64 && e->NW != 128 && e->NW != 256) e->NW = 256;
   auto smem_for = [&](int tw) { return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h).total; };
   const int budget = env_int("BRS_SMEM_BUDGET", 72 * 1024);
-  int tw = std::max(1, (e->T + tasks - 1) / tasks);
-  tw = std::min(tw, 64);
-  // keep at least ~4 tiles per resident CTA slot so that the dynamic scheduler can balance
-  tw = std::min(tw, std::max(1, cfg->n_worlds / (e->sm_count * 8)));
-  while (tw > 1 && smem_for(tw) > budget) --tw;
+  // as many worlds per tile as the budget allows (amortises barriers, fills the lanes
+  // of the per-robot phases), but keep >= ~8 tiles per SM for the dynamic scheduler
+  int tw_max = std::min(64, std::max(1, cfg->n_worlds / (e->sm_count * 8)));
+  while (tw_max > 1 && smem_for(tw_max) > budget) --tw_max;
+  // among tw <= tw_max prefer the one whose ray tasks fill whole passes of the workers
+  int tw = tw_max;
+  {
+    double best = -1;
+    for (int t = tw_max; t >= std::max(1, tw_max / 2); --t) {
+      const int n = t * tasks, passes = (n + e->NW - 1) / e->NW;
+      const double eff = (double)n / ((double)passes * e->NW);
+      if (eff > best + 0.02) { best = eff; tw = t; }
+    }
+  }
   tw = env_int("BRS_TW", tw);
   tw = std::max(1, std::min(tw, cfg->n_worlds));
   e->TW = tw;
@@ -354,12 +410,14 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     return fail(BRS_ERR_UNSUPPORTED, "brs_create: world too large for one CTA's shared memory (seg_cap / camera width / groups)");
   }
   e->n_tiles = (cfg->n_worlds + tw - 1) / tw;
-  e->GS = std::min(e->T, std::max(8, pow2ceil(cfg->seg_cap)));
-  e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->T / (gtasks * tw), 1))) : 1;
-  e->SLD = dtasks ? std::min(32, pow2floor(std::max(e->T / (dtasks * tw), 1))) : 1;
+  e->NH = 1;  // one helper warp prepares the next tile (launch bound: NW + 32 <= 288 threads)
+  e->T = e->NW + 32 * e->NH;
+  e->GS = std::min(e->NW, std::max(8, pow2ceil(cfg->seg_cap)));
+  e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * tw), 1))) : 1;
+  e->SLD = dtasks ? std::min(32, pow2floor(std::max(e->NW / (dtasks * tw), 1))) : 1;
   {
     const int Q = std::max(e->cam_w / 4, 1);
-    const int slots = std::max(e->T / Q, 1);
+    const int slots = std::max(e->NW / Q, 1);
     const int nislot = std::max(1, std::min(tw * std::max(cfg->n_camera, 1), slots));
     e->paint_rs = std::max(1, slots / nislot);
   }
@@ -457,6 +515,17 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.cam_w = e->cam_w; p.cam_h = e->cam_h;
   p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
   p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.paint_rs = e->paint_rs;
+  p.NW = e->NW; p.NH = e->NH;
+  {
+    const int R = c.n_robots, nvis = c.seg_cap + 4 * R;
+    p.dR = make_fastdiv(R); p.dSC = make_fastdiv(c.seg_cap); p.dTab = make_fastdiv(std::max(e->n_group * nvis, 1));
+    p.dNvis = make_fastdiv(nvis); p.dPair = make_fastdiv(R * R * 2); p.dNG = make_fastdiv(std::max(e->n_group, 1));
+    const bool cam = (flags & BRS_STEP_CAMERA) && c.n_camera > 0, sense = flags & BRS_STEP_SENSE;
+    const int cblocks = cam ? c.n_camera * (e->cam_w / e->NR) : 0;
+    p.dGT = make_fastdiv(std::max(cblocks + (sense ? e->n_gr : 0), 1));
+    p.dDT = make_fastdiv(std::max(e->n_dr + c.n_light + c.n_smell, 1));
+    p.dCpb = make_fastdiv(std::max(e->cam_w / std::max(e->NR, 1), 1));
+  }
   p.cull_margin = 0.05f;
   p.flags = flags;
   p.dt = time_step; p.smell_cell = c.smell_cell_size; p.light_mult = c.light_multiplier;

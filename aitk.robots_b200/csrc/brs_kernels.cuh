@@ -69,10 +69,30 @@ struct PointDev {
   int robot, _pad;
   double mx, my;
 };
-struct GroupDev {  // rays sharing one origin: robot + mount offset
-  int robot, _pad;
+struct GroupDev {  // rays sharing one origin: robot + mount offset, and what they can reach
+  int robot, has_cone;
   double mx, my;
+  // cone that contains every ray of the group, robot frame, widened by a margin:
+  // unit vectors of its lower / upper boundary and of its axis (has_cone: width < 180 deg)
+  float lo_c, lo_s, hi_c, hi_s, ax_c, ax_s;
+  float range;  // longest ray of the group, widened by a margin
+  float _pad;
 };
+struct __align__(16) GroupCull {  // per (world, group), world frame
+  float lo_x, lo_y, hi_x, hi_y, ax_x, ax_y, range2;
+  int has_cone;
+};
+
+// n / d for n * d < 2^32 as one multiply-high (host precomputes ceil(2^32 / d))
+struct FastDiv {
+  uint32_t mul, one;
+};
+__host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.one = d <= 1u;
+  f.mul = d <= 1u ? 0u : (uint32_t)((0x100000000ull + d - 1) / d);
+  return f;
+}
 
 struct KParams {
   int n_worlds, n_robots, seg_cap, n_bulbs, grid_w, grid_h;
@@ -84,6 +104,9 @@ struct KParams {
   int SLG, SLD;      // lanes per ray task: group path, direct path (powers of two <= 32)
   int n_gr, n_dr;    // range sensors on the group path / on the direct path
   int paint_rs;      // row slots of the paint phase
+  int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
+  int NH;            // helper warps: prepare the next tile during the SENSE phase
+  FastDiv dR, dSC, dTab, dNvis, dPair, dGT, dDT, dCpb, dNG;
   unsigned flags;
   double dt, smell_cell, light_mult;
   float cull_margin;
@@ -139,7 +162,7 @@ struct __align__(16) Strip {
 
 // shared memory carve-up, byte offsets; mirrored on the host for the launch size
 struct SmemLayout {
-  int raw[2], segtab, gtab, ws, org, cflag, meta, colinfo, strips, camcs, rowsky, rowgnd, mbar, sched, total;
+  int raw[2], segtab[2], gtab, gidx, gcnt, gcull, ws[2], org, cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, mbar, sched, total;
 };
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, int n_group, int n_camera, int cam_w,
@@ -148,13 +171,15 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   const int nvis = seg_cap + 4 * R;
   int o = 0;
   for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += TW * 5 * seg_cap * 4; o = align_up(o, 128); }
-  L.segtab = o; o += TW * nvis * 16;
+  for (int b = 0; b < 2; ++b) { L.segtab[b] = o; o += TW * nvis * 16; }
   L.gtab = o; o += TW * n_group * nvis * 16;
-  L.ws = o; o += TW * R * BRS_WS_STRIDE * 8;
+  L.gcull = o; o += TW * n_group * 32;
+  L.gcnt = o; o += align_up(TW * n_group * 8, 16);
+  L.gidx = o; o += align_up(TW * n_group * nvis * 2, 16);
+  for (int b = 0; b < 2; ++b) { L.ws[b] = o; o += TW * R * BRS_WS_STRIDE * 8; }
   L.org = o; o += TW * (n_group > 0 ? n_group : 1) * 16;
-  L.cflag = o; o += TW * R * 16;  // wall hit, pair_old mask, pair_new mask, stalled
-  L.meta = o; o += TW * 8;        // int S; float world extent
-  o = align_up(o, 16);
+  for (int b = 0; b < 2; ++b) { L.cflag[b] = o; o += TW * R * 16; }  // wall hit, pair_old mask, pair_new mask, stalled
+  for (int b = 0; b < 2; ++b) { L.meta[b] = o; o += align_up(TW * 8, 16); }  // int S; float world extent
   L.colinfo = o; o += TW * n_camera * cam_w * (int)sizeof(ColInfo);
   L.strips = o; o += TW * n_camera * cam_w * 4 * (R - 1) * (int)sizeof(Strip);
   o = align_up(o, 16);
@@ -266,12 +291,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // is nearer, starts at bits(1.0f): only hits with t <= 1 (inside the range)
 // win.  Negative or NaN-free by construction (degenerate entries are zero).
 #define BRS_GKEY_INIT 0x3F800000u
-template <int NR>
-__device__ __forceinline__ void search_group(const float4* __restrict__ tab, int j0, int j1, int g, int SL,
+template <int NR, bool SL1>
+__device__ __forceinline__ void search_group(const float4* __restrict__ tab, int j0, int j1, int g, int SLrt,
                                              const float (&rx)[NR], const float (&ry)[NR], uint32_t (&key)[NR],
                                              int (&idx)[NR]) {
+  const int SL = SL1 ? 1 : SLrt;
 #pragma unroll 4
-  for (int j = j0 + g; j < j1; j += SL) {
+  for (int j = j0 + (SL1 ? 0 : g); j < j1; j += SL) {
     const float4 s = tab[j];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
@@ -301,10 +327,12 @@ __device__ __forceinline__ void group_max(uint32_t& key, int& idx, int SL, uint3
 // the ray parameter t (unsigned order == float order for t >= 0; negative / NaN
 // / inf parameters compare above BRS_KEY_NOHIT), smaller is nearer.
 #define BRS_KEY_NOHIT 0x3F800001u  // just above 1.0f: parameters <= 1 are hits
-__device__ __forceinline__ void search_direct(const float4* __restrict__ segtab, int j0, int j1, int g, int SL,
+template <bool SL1>
+__device__ __forceinline__ void search_direct(const float4* __restrict__ segtab, int j0, int j1, int g, int SLrt,
                                               float ox, float oy, float rx, float ry, uint32_t& key, int& idx) {
+  const int SL = SL1 ? 1 : SLrt;
 #pragma unroll 4
-  for (int j = j0 + g; j < j1; j += SL) {
+  for (int j = j0 + (SL1 ? 0 : g); j < j1; j += SL) {
     const float4 s = segtab[j];
     const float dx = ox - s.x, dy = oy - s.y;
     const float den = s.w * rx - s.z * ry;
@@ -474,19 +502,93 @@ __device__ __forceinline__ void camera_column(const KParams& p, const CameraDev&
 // ------------------------------------------------------------------------------
 // The fused World.step kernel.  NR = camera columns per thread.
 // ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f.one ? n : __umulhi(n, f.mul); }
+
+// PREP of one tile, run by `nth` helper threads (index ht): robot state HBM ->
+// shared, heading trig, proposed pose and velocity, committed and proposed box
+// corners (compute_boundingbox), collision flags cleared, per-world meta and the
+// FP32 table of the static walls (start point and delta) from the TMA-landed store.
+__device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
+                                             const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
+                                             double* __restrict__ wsb, int4* __restrict__ cflag,
+                                             int2* __restrict__ meta) {
+  const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
+  for (int i = ht; i < nw * R; i += nth) {
+    const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
+    const RobotDev& rd = p.robots[r];
+    double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
+    const size_t o = ((size_t)w * R + r) * 3;
+    const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
+    const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
+    wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
+    wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
+    double s0, c0;
+    sincos(a, &s0, &c0);
+    wsr[BRS_WS_RCS] = c0;
+    wsr[BRS_WS_RCS + 1] = s0;
+    double px = x, py = y, c1 = c0, s1 = s0;
+    double* pr = wsr + BRS_WS_PROP;
+    if (do_move) {
+      const double* tv = p.tvel + o;
+      const double vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
+      const double vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
+      const double va = deltav(tv[2], v2, rd.va_ramp, p.dt);
+      const double pa = ds(a, dm(va, p.dt));
+      const double ang = da(-pa, BRS_PI_OVER_2);
+      double sn, cs;
+      sincos(ang, &sn, &cs);
+      // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
+      const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
+      const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
+      px = da(x, tvx);
+      py = da(y, tvy);
+      c1 = sn;  // sin(pi/2 - pa) = cos(pa)
+      s1 = cs;  // cos(pi/2 - pa) = sin(pa)
+      pr[8] = px; pr[9] = py; pr[10] = pa;
+      pr[11] = vx; pr[12] = vy; pr[13] = va;
+      pr[14] = c1; pr[15] = s1;
+    }
+    // corner = centre + R(heading) * (corner offset in the a=0 frame)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double ox = rd.cox[k], oy = rd.coy[k];
+      wsr[BRS_WS_DBOX + 2 * k] = da(x, ds(dm(c0, ox), dm(s0, oy)));
+      wsr[BRS_WS_DBOX + 2 * k + 1] = da(y, da(dm(s0, ox), dm(c0, oy)));
+      if (do_move) {
+        pr[2 * k] = da(px, ds(dm(c1, ox), dm(s1, oy)));
+        pr[2 * k + 1] = da(py, da(dm(s1, ox), dm(c1, oy)));
+      }
+    }
+    cflag[i] = make_int4(0, 0, 0, 0);
+  }
+  for (int wl = ht; wl < nw; wl += nth) {
+    const int w = w0 + wl;
+    meta[wl].x = min(max(p.seg_count[w], 0), SC);
+    meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
+  }
+  for (int i = ht; i < nw * SC; i += nth) {
+    const int wl = (int)fdiv(i, p.dSC), j = i - wl * SC;
+    const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+    const float x1 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[SC + j]);
+    const float x2 = __uint_as_float(raw[2 * SC + j]), y2 = __uint_as_float(raw[3 * SC + j]);
+    segtab[(size_t)wl * nvis + j] = make_float4(x1, y1, x2 - x1, y2 - y1);
+  }
+}
+
 template <int NR>
-__global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int NW = p.NW;              // worker threads of the SENSE phase
+  const int NHT = NT - NW;          // helper threads (>= 32)
   const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
   const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
   const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h);
-  float4* const segtab = (float4*)(smem + L.segtab);
   float4* const gtab = (float4*)(smem + L.gtab);
-  double* const wsb = (double*)(smem + L.ws);
+  uint16_t* const gidx = (uint16_t*)(smem + L.gidx);
+  int2* const gcnt = (int2*)(smem + L.gcnt);
+  GroupCull* const gcull = (GroupCull*)(smem + L.gcull);
   double2* const org = (double2*)(smem + L.org);
-  int4* const cflag = (int4*)(smem + L.cflag);
-  int2* const meta = (int2*)(smem + L.meta);
   ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
   Strip* const strips = (Strip*)(smem + L.strips);
   double2* const camcs = (double2*)(smem + L.camcs);
@@ -498,7 +600,7 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
   const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
   const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
 
-  // ---- prologue: barriers, first two tiles, camera tables ----------------------
+  // ---- prologue: barriers, TMA of the first tile, camera tables, PREP of the first tile
   if (tid == 0) {
     mbar_init(smem_u32(&mbar[0]), 1);
     mbar_init(smem_u32(&mbar[1]), 1);
@@ -517,12 +619,31 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
     rowgnd[i] = p.row_gnd[i];
   }
   __syncthreads();
+  {
+    const int t0 = sched[0];
+    if (t0 < p.n_tiles) {
+      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
+      mbar_wait(smem_u32(&mbar[0]), 0);
+      prepare_tile(p, w0, nw, tid, NT, do_move, (const uint32_t*)(smem + L.raw[0]), (float4*)(smem + L.segtab[0]),
+                   (double*)(smem + L.ws[0]), (int4*)(smem + L.cflag[0]), (int2*)(smem + L.meta[0]));
+    }
+  }
+  __syncthreads();
+
+  // paint mapping: worker thread -> (picture slot, row slot, column quad)
+  const int pQ = max(p.cam_w >> 2, 1);
+  const int p_q = tid % pQ, p_rest = tid / pQ, p_RS = p.paint_rs;
+  const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQ) / p_RS;
 
   int it = 0;
   for (int tile = sched[0]; tile < p.n_tiles; ++it) {
     const int buf = it & 1;
     const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
     const uint32_t* const rawb = (const uint32_t*)(smem + L.raw[buf]);
+    float4* const segtab = (float4*)(smem + L.segtab[buf]);
+    double* const wsb = (double*)(smem + L.ws[buf]);
+    int4* const cflag = (int4*)(smem + L.cflag[buf]);
+    const int2* const meta = (const int2*)(smem + L.meta[buf]);
     // fetch the next tile index and start its TMA into the other buffer (free
     // since the barrier that ended the previous iteration)
     if (tid == 0) {
@@ -535,74 +656,8 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
                      smem_u32(&mbar[buf ^ 1]));
       }
     }
-
-    // ---------------- phase 1: PREP ------------------------------------------------
-    // thread per (world, robot): state HBM -> shared, heading trig, proposed pose and
-    // velocity, committed and proposed box corners (compute_boundingbox)
-    for (int i = tid; i < nw * R; i += NT) {
-      const int wl = i / R, r = i - wl * R, w = w0 + wl;
-      const RobotDev& rd = p.robots[r];
-      double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
-      const size_t o = ((size_t)w * R + r) * 3;
-      const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
-      const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
-      wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
-      wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
-      double s0, c0;
-      sincos(a, &s0, &c0);
-      wsr[BRS_WS_RCS] = c0;
-      wsr[BRS_WS_RCS + 1] = s0;
-      double px = x, py = y, c1 = c0, s1 = s0;
-      double* pr = wsr + BRS_WS_PROP;
-      if (do_move) {
-        const double* tv = p.tvel + o;
-        const double vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
-        const double vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
-        const double va = deltav(tv[2], v2, rd.va_ramp, p.dt);
-        const double pa = ds(a, dm(va, p.dt));
-        const double ang = da(-pa, BRS_PI_OVER_2);
-        double sn, cs;
-        sincos(ang, &sn, &cs);
-        // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
-        const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
-        const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
-        px = da(x, tvx);
-        py = da(y, tvy);
-        c1 = sn;  // sin(pi/2 - pa) = cos(pa)
-        s1 = cs;  // cos(pi/2 - pa) = sin(pa)
-        pr[8] = px; pr[9] = py; pr[10] = pa;
-        pr[11] = vx; pr[12] = vy; pr[13] = va;
-        pr[14] = c1; pr[15] = s1;
-      }
-      // corner = centre + R(heading) * (corner offset in the a=0 frame)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double ox = rd.cox[k], oy = rd.coy[k];
-        wsr[BRS_WS_DBOX + 2 * k] = da(x, ds(dm(c0, ox), dm(s0, oy)));
-        wsr[BRS_WS_DBOX + 2 * k + 1] = da(y, da(dm(s0, ox), dm(c0, oy)));
-        if (do_move) {
-          pr[2 * k] = da(px, ds(dm(c1, ox), dm(s1, oy)));
-          pr[2 * k + 1] = da(py, da(dm(s1, ox), dm(c1, oy)));
-        }
-      }
-      cflag[i] = make_int4(0, 0, 0, 0);
-    }
-    for (int wl = tid; wl < nw; wl += NT) {
-      const int w = w0 + wl;
-      meta[wl].x = min(max(p.seg_count[w], 0), SC);
-      meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
-    }
-    // the wall store of this tile has landed (every thread observes the phase itself)
+    // every thread observes the phase of this tile's wall store itself before reading it
     mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
-    // FP32 segment table of the static walls: start point and delta
-    for (int i = tid; i < nw * SC; i += NT) {
-      const int wl = i / SC, j = i - wl * SC;
-      const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
-      const float x1 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[SC + j]);
-      const float x2 = __uint_as_float(raw[2 * SC + j]), y2 = __uint_as_float(raw[3 * SC + j]);
-      segtab[(size_t)wl * nvis + j] = make_float4(x1, y1, x2 - x1, y2 - y1);
-    }
-    __syncthreads();
 
     if (do_move) {
       // ---------------- phase 2: COLLIDE ---------------------------------------------
@@ -611,35 +666,66 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
       // margin far above FP32 error), then the exact FP64 4-edge test.
       {
         const int GS = p.GS, gi = tid / GS, gl = tid - gi * GS, ngrp = NT / GS;
-        for (int i = gi; i < nw * R; i += ngrp) {
-          const int wl = i / R, r = i - wl * R;
-          const int S = meta[wl].x;
-          const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
-          const float cx = (float)pr[8], cy = (float)pr[9];
-          const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
-          const float rad2 = rad * rad;
-          const float4* st = segtab + (size_t)wl * nvis;
-          bool hit = false;
-          for (int j = gl; j < S; j += GS) {
-            const float4 s = st[j];
-            const float ax = cx - s.x, ay = cy - s.y;
-            const float ee = fmaf(s.z, s.z, s.w * s.w);
-            float h = fmaf(ax, s.z, ay * s.w) * rcp_approx(ee);
-            h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
-            const float vx = fmaf(-h, s.z, ax), vy = fmaf(-h, s.w, ay);
-            if (fmaf(vx, vx, vy * vy) <= rad2) {
-              const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
-              const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
-              const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
+        if (gi < ngrp) {
+          for (int i = gi; i < nw * R; i += ngrp) {
+            const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
+            const int S = meta[wl].x;
+            const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
+            const float cx = (float)pr[8], cy = (float)pr[9];
+            const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
+            const float rad2 = rad * rad;
+            const float cscale = 4e-7f * (fabsf(cx) + fabsf(cy) + rad + 1.f);
+            const float4* st = segtab + (size_t)wl * nvis;
+            float pc[8], pe[8];  // proposed corners and edge vectors, FP32
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int e2 = (e + 1) & 3;
-                hit |= isect64_bool(pr[2 * e], pr[2 * e + 1], ds(pr[2 * e2], pr[2 * e]),
-                                    ds(pr[2 * e2 + 1], pr[2 * e + 1]), x3, y3, x4, y4);
+            for (int e = 0; e < 4; ++e) {
+              const int e2 = (e + 1) & 3;
+              pc[2 * e] = (float)pr[2 * e];
+              pc[2 * e + 1] = (float)pr[2 * e + 1];
+              pe[2 * e] = (float)(pr[2 * e2] - pr[2 * e]);
+              pe[2 * e + 1] = (float)(pr[2 * e2 + 1] - pr[2 * e + 1]);
+            }
+            bool hit = false;
+            for (int j = gl; j < S; j += GS) {
+              const float4 s = st[j];
+              const float ax = cx - s.x, ay = cy - s.y;
+              const float ee = fmaf(s.z, s.z, s.w * s.w);
+              float h = fmaf(ax, s.z, ay * s.w) * rcp_approx(ee);
+              h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
+              const float vx = fmaf(-h, s.z, ax), vy = fmaf(-h, s.w, ay);
+              if (fmaf(vx, vx, vy * vy) <= rad2) {
+                // inside the disc: classify the 4 edges in FP32 against the segment widened
+                // by a margin far above FP32 error; only an edge that is not a certain miss
+                // pays for the exact FP64 test
+                bool maybe = false;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float bx = pc[2 * e] - s.x, by = pc[2 * e + 1] - s.y;  // edge start relative to the wall start
+                  const float den = s.w * pe[2 * e] - s.z * pe[2 * e + 1];
+                  const float na = s.z * by - s.w * bx, nb = pe[2 * e] * by - pe[2 * e + 1] * bx;
+                  // error bound: coordinates carry ~6e-8 * |coordinate| of FP32 rounding, which the
+                  // cross products scale by the edge / wall lengths; products add ~1e-7 relative
+                  const float ad = fabsf(den);
+                  const float tol = cscale * (fabsf(s.z) + fabsf(s.w) + fabsf(pe[2 * e]) + fabsf(pe[2 * e + 1])) +
+                                    1e-5f * (fabsf(na) + fabsf(nb) + ad);
+                  const float sa_ = den < 0.f ? -na : na, sb_ = den < 0.f ? -nb : nb;
+                  maybe |= !(sa_ < -tol || sa_ > ad + tol || sb_ < -tol || sb_ > ad + tol);
+                }
+                if (maybe) {
+                  const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+                  const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
+                  const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int e2 = (e + 1) & 3;
+                    hit |= isect64_bool(pr[2 * e], pr[2 * e + 1], ds(pr[2 * e2], pr[2 * e]),
+                                        ds(pr[2 * e2 + 1], pr[2 * e + 1]), x3, y3, x4, y4);
+                  }
+                }
               }
             }
+            if (hit) cflag[i].x = 1;
           }
-          if (hit) cflag[i].x = 1;
         }
       }
       // robots: proposal i against the committed box of o (pair_old) and, for o < i,
@@ -647,8 +733,8 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
       if (R > 1) {
         const int per_world = R * R * 2;
         for (int i = tid; i < nw * per_world; i += NT) {
-          const int wl = i / per_world, k = i - wl * per_world;
-          const int ri = k / (2 * R), ro = (k >> 1) % R, v = k & 1;
+          const int wl = (int)fdiv(i, p.dPair), k = i - wl * per_world;
+          const int ri = (int)fdiv(k >> 1, p.dR), ro = (k >> 1) - ri * R, v = k & 1;
           if (ro == ri || (v && ro > ri)) continue;
           const double* wi = wsb + (size_t)(wl * R + ri) * BRS_WS_STRIDE;
           const double* wo = wsb + (size_t)(wl * R + ro) * BRS_WS_STRIDE;
@@ -673,11 +759,17 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
         }
       }
       __syncthreads();
+    }
 
-      // ---------------- phase 3: COMMIT ----------------------------------------------
-      // thread per (world, robot): replay the list order on the masks, commit or stall
-      for (int i = tid; i < nw * R; i += NT) {
-        const int wl = i / R, r = i - wl * R, w = w0 + wl;
+    // ---------------- phase 3: COMMIT ----------------------------------------------
+    // thread per (world, robot): replay the list order on the masks, commit or stall,
+    // then publish everything that hangs off the final pose: the box as FP32 search
+    // segments and the origins of the robot's ray groups.  (During this phase nobody
+    // reads DBOX / POSE / RCS of another robot: the replay only reads the masks.)
+    for (int i = tid; i < nw * R; i += NT) {
+      const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
+      double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
+      if (do_move) {
         unsigned stalled_mask = 0;
         bool hit = false;
         for (int q = 0; q <= r; ++q) {
@@ -689,7 +781,6 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
           hit = f.x || m;
           if (hit) stalled_mask |= 1u << q;
         }
-        double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
         const double* pr = wsr + BRS_WS_PROP;
         const size_t o = ((size_t)w * R + r) * 3;
         if (!hit) {
@@ -701,81 +792,140 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
           }
           wsr[BRS_WS_RCS] = pr[14];
           wsr[BRS_WS_RCS + 1] = pr[15];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) wsr[BRS_WS_DBOX + k] = pr[k];
         } else {
 #pragma unroll
           for (int k = 0; k < 3; ++k) p.vel[o + k] = 0.0;
         }
         p.stalled[(size_t)w * R + r] = (uint8_t)(hit ? 1 : 0);
-        cflag[i].w = hit ? 1 : 0;
       }
-      __syncthreads();
-      // moved robots take their proposed box (nobody reads DBOX as "old" any more)
-      for (int i = tid; i < nw * R * 8; i += NT) {
-        const int ir = i >> 3, k = i & 7;
-        if (!cflag[ir].w) wsb[(size_t)ir * BRS_WS_STRIDE + BRS_WS_DBOX + k] = wsb[(size_t)ir * BRS_WS_STRIDE + BRS_WS_PROP + k];
+      if (do_sense || do_cam) {
+        const double* box = wsr + BRS_WS_DBOX;
+        float4* dst = segtab + (size_t)wl * nvis + meta[wl].x + 4 * r;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int e2 = (e + 1) & 3;
+          const float x1 = (float)box[2 * e], y1 = (float)box[2 * e + 1];
+          const float x2 = (float)box[2 * e2], y2 = (float)box[2 * e2 + 1];
+          dst[e] = make_float4(x1, y1, x2 - x1, y2 - y1);
+        }
+        for (int g = 0; g < NG; ++g) {
+          const GroupDev& gd = p.groups[g];
+          if (gd.robot != r) continue;
+          double x1, y1, ca, sa;
+          mount_point(wsr, gd.mx, gd.my, x1, y1, ca, sa);
+          org[wl * NG + g] = make_double2(x1, y1);
+          const float cf = (float)ca, sf = (float)sa;
+          GroupCull gc;
+          gc.lo_x = cf * gd.lo_c - sf * gd.lo_s; gc.lo_y = sf * gd.lo_c + cf * gd.lo_s;
+          gc.hi_x = cf * gd.hi_c - sf * gd.hi_s; gc.hi_y = sf * gd.hi_c + cf * gd.hi_s;
+          gc.ax_x = cf * gd.ax_c - sf * gd.ax_s; gc.ax_y = sf * gd.ax_c + cf * gd.ax_s;
+          gc.range2 = gd.range * gd.range;
+          gc.has_cone = gd.has_cone;
+          gcull[wl * NG + g] = gc;
+        }
       }
-      __syncthreads();
     }
+    __syncthreads();
 
     if (do_sense || do_cam) {
-      // robot boxes as FP32 search segments; origins of the ray groups
-      for (int i = tid; i < nw * R * 4; i += NT) {
-        const int ir = i >> 2, e = i & 3, e2 = (e + 1) & 3, wl = ir / R, r = ir - wl * R;
-        const double* box = wsb + (size_t)ir * BRS_WS_STRIDE + BRS_WS_DBOX;
-        const float x1 = (float)box[2 * e], y1 = (float)box[2 * e + 1];
-        const float x2 = (float)box[2 * e2], y2 = (float)box[2 * e2 + 1];
-        segtab[(size_t)wl * nvis + meta[wl].x + 4 * r + e] = make_float4(x1, y1, x2 - x1, y2 - y1);
-      }
-      for (int i = tid; i < nw * NG; i += NT) {
-        const int wl = i / NG, g = i - wl * NG;
-        const GroupDev& gd = p.groups[g];
-        double x1, y1, ca, sa;
-        mount_point(wsb + (size_t)(wl * R + gd.robot) * BRS_WS_STRIDE, gd.mx, gd.my, x1, y1, ca, sa);
-        org[i] = make_double2(x1, y1);
-      }
-      __syncthreads();
-
       // ---------------- phase 4: TABLE -------------------------------------------------
       // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,
-      // na = ex*dy - ey*dx.  The own robot's edges and degenerate entries are zero (no hit).
+      // na = ex*dy - ey*dx.  Entries no ray of the group can hit are dropped: the own
+      // robot's edges, degenerate ones (origin on the wall's line), walls whose line is
+      // out of the group's range, walls entirely outside the cone of its rays (all three
+      // conservative, with margins far above FP32 error).  Survivors are then compacted
+      // in index order by one warp per (world, group), so the search loops over fewer
+      // entries and ties still resolve as in the reference.
       if (NG > 0) {
         const int per_world = NG * nvis;
         for (int i = tid; i < nw * per_world; i += NT) {
-          const int wl = i / per_world, k = i - wl * per_world;
-          const int g = k / nvis, j = k - g * nvis;
+          const int wl = (int)fdiv(i, p.dTab), k = i - wl * per_world;
+          const int g = (int)fdiv(k, p.dNvis), j = k - g * nvis;
           const int S = meta[wl].x, nv = S + 4 * R;
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
           if (j < nv && !(j >= S && ((j - S) >> 2) == p.groups[g].robot)) {
             const float4 s = segtab[(size_t)wl * nvis + j];
             const double2 O = org[wl * NG + g];
+            const GroupCull gc = gcull[wl * NG + g];
             const float dx = (float)(O.x - (double)s.x), dy = (float)(O.y - (double)s.y);
             const float na = fmaf(s.z, dy, -(s.w * dx));
-            if (fabsf(na) > 1e-30f) {
-              const float inv = 1.0f / na;
+            const float ee = fmaf(s.z, s.z, s.w * s.w);
+            bool keep = fabsf(na) > 1e-30f && na * na <= gc.range2 * ee;  // distance to the wall's line
+            if (gc.has_cone) {
+              const float ax = -dx, ay = -dy, bx = s.z - dx, by = s.w - dy;  // end points seen from the origin
+              const bool out_lo = (gc.lo_x * ay - gc.lo_y * ax < 0.f) && (gc.lo_x * by - gc.lo_y * bx < 0.f);
+              const bool out_hi = (ax * gc.hi_y - ay * gc.hi_x < 0.f) && (bx * gc.hi_y - by * gc.hi_x < 0.f);
+              const bool behind = (gc.ax_x * ax + gc.ax_y * ay < 0.f) && (gc.ax_x * bx + gc.ax_y * by < 0.f);
+              keep = keep && !(out_lo || out_hi || behind);
+            }
+            if (keep) {
+              const float inv = rcp_approx(na);
               t = make_float4(s.w * inv, -s.z * inv, dx * inv, dy * inv);
             }
           }
           gtab[(size_t)wl * per_world + k] = t;
         }
         __syncthreads();
+        // order-preserving in-place compaction: position <= index, chunks ascend
+        {
+          const int warp = tid >> 5, nwarp = NT >> 5;
+          for (int pg = warp; pg < nw * NG; pg += nwarp) {
+            const int wl = (int)fdiv(pg, p.dNG);
+            const int S = meta[wl].x, nv = S + 4 * R;
+            float4* tab = gtab + (size_t)pg * nvis;
+            uint16_t* ix = gidx + (size_t)pg * nvis;
+            int base = 0, cw = 0;
+            for (int j0 = 0; j0 < nv; j0 += 32) {
+              const int j = j0 + lane;
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (j < nv) t = tab[j];
+              const bool keep = (t.x != 0.f) || (t.y != 0.f);
+              const unsigned bal = __ballot_sync(0xffffffffu, keep);
+              const int pos = base + __popc(bal & ((1u << lane) - 1u));
+              __syncwarp();
+              if (keep) {
+                tab[pos] = t;
+                ix[pos] = (uint16_t)j;
+              }
+              const int nwall = S - j0;  // lanes below this index hold walls
+              cw += __popc(nwall >= 32 ? bal : (nwall <= 0 ? 0u : (bal & ((1u << nwall) - 1u))));
+              base += __popc(bal);
+            }
+            if (lane == 0) gcnt[pg] = make_int2(cw, base);
+          }
+        }
+        __syncthreads();
       }
+    }
 
-      // ---------------- phase 5: SENSE ---------------------------------------------------
+    // ---------------- phase 5: SENSE (workers) + PREP of the next tile (helpers) ----------
+    if (tid >= NW) {
+      const int tn = sched[1 + (buf ^ 1)];  // written before the barriers above
+      if (tn < p.n_tiles) {
+        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
+        mbar_wait(smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
+        prepare_tile(p, wn, nn, tid - NW, NHT, do_move, (const uint32_t*)(smem + L.raw[buf ^ 1]),
+                     (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
+                     (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]));
+      }
+    } else if (do_sense || do_cam) {
       // 5a. group path: camera column blocks, then grouped range sensors
       {
-        const int SL = p.SLG, g = tid & (SL - 1), slot = tid / SL, nslot = NT / SL;
+        const int SL = p.SLG, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
         const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
         const int cblocks = do_cam ? p.n_camera * (p.cam_w / NR) : 0;
         const int ngr = do_sense ? p.n_gr : 0;
         const int ntask = cblocks + ngr;
         for (int i = slot; i < nw * ntask; i += nslot) {
-          const int wl = i / ntask, task = i - wl * ntask, w = w0 + wl;
+          const int wl = (int)fdiv(i, p.dGT), task = i - wl * ntask, w = w0 + wl;
           const int S = meta[wl].x;
           const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
           const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
           if (task < cblocks) {
             const int cpb = p.cam_w / NR;  // column blocks per camera
-            const int c = task / cpb, col0 = (task - c * cpb) * NR;
+            const int c = (int)fdiv(task, p.dCpb), col0 = (task - c * cpb) * NR;
             const CameraDev& cd = p.cameras[c];
             const int r = cd.robot;
             const double2 O = org[wl * NG + cd.group];
@@ -797,13 +947,20 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
               idx[k] = -1;
             }
             // walls only (height == 1); other robots become strips below
-            search_group<NR>(gtab + ((size_t)wl * NG + cd.group) * nvis, 0, S, g, SL, rx, ry, key, idx);
+            const int pg = wl * NG + cd.group;
+            const float4* tab = gtab + (size_t)pg * nvis;
+            const int cw = gcnt[pg].x;
+            if (SL == 1)
+              search_group<NR, true>(tab, 0, cw, 0, 1, rx, ry, key, idx);
+            else
+              search_group<NR, false>(tab, 0, cw, g, SL, rx, ry, key, idx);
             const double wsize = (double)__int_as_float(meta[wl].y);
 #pragma unroll
             for (int k = 0; k < NR; ++k) {
               if (SL > 1) group_max(key[k], idx[k], SL, gmask);
               if (g == 0) {
                 const size_t col = ((size_t)wl * p.n_camera + c) * p.cam_w + col0 + k;
+                if (idx[k] >= 0) idx[k] = gidx[(size_t)pg * nvis + idx[k]];
                 camera_column(p, cd, r, idx[k], raw, SC, S, ws, wsize, O.x, O.y, x2[k], y2[k], colinfo + col,
                               strips + col * strips_per_col);
               }
@@ -815,6 +972,9 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
             const int r = sd.robot;
             const double2 O = org[wl * NG + sd.group];
             const double ca = ws[r * BRS_WS_STRIDE + BRS_WS_RCS], sa = ws[r * BRS_WS_STRIDE + BRS_WS_RCS + 1];
+            const int pg = wl * NG + sd.group;
+            const float4* tab = gtab + (size_t)pg * nvis;
+            const int ct = gcnt[pg].y;
             double reading = 1.0;
             for (int k = 0; k < sd.n_rays; ++k) {
               const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
@@ -823,10 +983,13 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
               float rx[1] = {(float)ds(x2, O.x)}, ry[1] = {(float)ds(y2, O.y)};
               uint32_t key[1] = {BRS_GKEY_INIT};
               int idx[1] = {-1};
-              search_group<1>(gtab + ((size_t)wl * NG + sd.group) * nvis, 0, S + 4 * R, g, SL, rx, ry, key, idx);
+              if (SL == 1)
+                search_group<1, true>(tab, 0, ct, 0, 1, rx, ry, key, idx);
+              else
+                search_group<1, false>(tab, 0, ct, g, SL, rx, ry, key, idx);
               if (SL > 1) group_max(key[0], idx[0], SL, gmask);
               if (g == 0 && idx[0] >= 0) {
-                const double d = refine64(raw, SC, S, ws, idx[0], O.x, O.y, x2, y2);
+                const double d = refine64(raw, SC, S, ws, gidx[(size_t)pg * nvis + idx[0]], O.x, O.y, x2, y2);
                 if (d < dm(reading, sd.max)) reading = d / sd.max;
               }
             }
@@ -836,11 +999,11 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
       }
       // 5b. direct path: range sensors on their own mount, light and smell sensors
       if (do_sense) {
-        const int SL = p.SLD, g = tid & (SL - 1), slot = tid / SL, nslot = NT / SL;
+        const int SL = p.SLD, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
         const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
         const int ntask = p.n_dr + p.n_light + p.n_smell;
         for (int i = slot; i < nw * ntask; i += nslot) {
-          const int wl = i / ntask, task = i - wl * ntask, w = w0 + wl;
+          const int wl = (int)fdiv(i, p.dDT), task = i - wl * ntask, w = w0 + wl;
           const int S = meta[wl].x, nseg = S + 4 * R;
           const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
           const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
@@ -862,9 +1025,14 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
               const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
               uint32_t key = BRS_KEY_NOHIT;
               int idx = -1;
-              search_direct(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-              search_direct(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-              if (SL > 1) group_min(key, idx, SL, gmask);
+              if (SL == 1) {
+                search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
+                search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
+              } else {
+                search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+                search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+                group_min(key, idx, SL, gmask);
+              }
               if (g == 0 && idx >= 0) {
                 const double d = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2);
                 if (d < dm(reading, sd.max)) reading = d / sd.max;
@@ -889,9 +1057,14 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
               const float rx = (float)ex, ry = (float)ey;
               uint32_t key = BRS_KEY_NOHIT;
               int idx = -1;
-              search_direct(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-              search_direct(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-              if (SL > 1) group_min(key, idx, SL, gmask);
+              if (SL == 1) {
+                search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
+                search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
+              } else {
+                search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+                search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+                group_min(key, idx, SL, gmask);
+              }
               if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
             }
             if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
@@ -912,33 +1085,31 @@ __global__ void __launch_bounds__(256, 3) brs_step_kernel(const __grid_constant_
           }
         }
       }
+    }
 
-      // ---------------- phase 6: PAINT ---------------------------------------------------
-      if (do_cam) {
-        __syncthreads();
-        const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
-        const int nimg = nw * p.n_camera;
-        uint4* const out0 = (uint4*)(p.cam_out + (size_t)w0 * p.n_camera * (size_t)H * W * 4);
-        if (NT >= Q) {
-          // thread -> (picture slot, row slot, column quad): the 4 column records stay in
-          // registers over the rows, a warp writes whole 128-byte lines per store
-          const int q = tid % Q, rest = tid / Q, RS = p.paint_rs;
-          const int rslot = rest % RS, islot = rest / RS, nislot = (NT / Q) / RS;
-          if (islot < nislot) {
-            for (int im = islot; im < nimg; im += nislot)
-              paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
-                         strips_per_col, rowsky, rowgnd, q, Q, rslot, RS, H);
-          }
-        } else {
-          // picture wider than 4 x threads: several quads per thread
-          for (int im = 0; im < nimg; ++im)
-            for (int q = tid; q < Q; q += NT)
-              paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
-                         strips_per_col, rowsky, rowgnd, q, Q, 0, 1, H);
+    // ---------------- phase 6: PAINT ---------------------------------------------------
+    if (do_cam) {
+      __syncthreads();
+      const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
+      const int nimg = nw * p.n_camera;
+      uint4* const out0 = (uint4*)(p.cam_out + (size_t)w0 * p.n_camera * (size_t)H * W * 4);
+      if (NW >= Q) {
+        // worker thread -> (picture slot, row slot, column quad): the 4 column records stay
+        // in registers over the rows, a warp writes whole 128-byte lines per store
+        if (tid < NW && p_islot < p_nislot) {
+          for (int im = p_islot; im < nimg; im += p_nislot)
+            paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
+                       strips_per_col, rowsky, rowgnd, p_q, Q, p_rslot, p_RS, H);
         }
+      } else {
+        // picture wider than 4 x threads: several quads per thread
+        for (int im = 0; im < nimg; ++im)
+          for (int q = tid; q < Q; q += NT)
+            paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
+                       strips_per_col, rowsky, rowgnd, q, Q, 0, 1, H);
       }
     }
-    __syncthreads();  // tile done: its buffers are free, the next tile index is visible
+    __syncthreads();  // tile done: its buffers are free, the next tile is prepared
     tile = sched[1 + (buf ^ 1)];
   }
 
