@@ -162,7 +162,7 @@ struct __align__(16) Strip {
 
 // shared memory carve-up, byte offsets; mirrored on the host for the launch size
 struct SmemLayout {
-  int raw[2], segtab[2], gtab, gidx, gcnt, gcull, ws[2], org, cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, mbar, sched, total;
+  int raw[2], segtab[2], gtab, gidx, gcnt, gcull[2], ws[2], org[2], cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, mbar, sched, total;
 };
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, int n_group, int n_camera, int cam_w,
@@ -173,11 +173,11 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += TW * 5 * seg_cap * 4; o = align_up(o, 128); }
   for (int b = 0; b < 2; ++b) { L.segtab[b] = o; o += TW * nvis * 16; }
   L.gtab = o; o += TW * n_group * nvis * 16;
-  L.gcull = o; o += TW * n_group * 32;
+  for (int b = 0; b < 2; ++b) { L.gcull[b] = o; o += TW * n_group * 32; }
   L.gcnt = o; o += align_up(TW * n_group * 8, 16);
   L.gidx = o; o += align_up(TW * n_group * nvis * 2, 16);
   for (int b = 0; b < 2; ++b) { L.ws[b] = o; o += TW * R * BRS_WS_STRIDE * 8; }
-  L.org = o; o += TW * (n_group > 0 ? n_group : 1) * 16;
+  for (int b = 0; b < 2; ++b) { L.org[b] = o; o += TW * (n_group > 0 ? n_group : 1) * 16; }
   for (int b = 0; b < 2; ++b) { L.cflag[b] = o; o += TW * R * 16; }  // wall hit, pair_old mask, pair_new mask, stalled
   for (int b = 0; b < 2; ++b) { L.meta[b] = o; o += align_up(TW * 8, 16); }  // int S; float world extent
   L.colinfo = o; o += TW * n_camera * cam_w * (int)sizeof(ColInfo);
@@ -501,8 +501,19 @@ __device__ __forceinline__ void camera_column(const KParams& p, const CameraDev&
 
 // ------------------------------------------------------------------------------
 // The fused World.step kernel.  NR = camera columns per thread.
+//
+// Warp specialisation: the HELPER team (threads >= NW) runs Robot.step -- PREP,
+// COLLIDE, COMMIT -- of tile n+1 while the WORKERS (threads < NW) run the sensors
+// and pictures -- TABLE, SENSE, PAINT -- of tile n.  The teams meet once per tile
+// (__syncthreads); inside a team phases are separated by named barriers.
 // ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f.one ? n : __umulhi(n, f.mul); }
+__device__ __forceinline__ void team_sync(int id, int nthreads) {
+  if (nthreads == 32)
+    __syncwarp();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // PREP of one tile, run by `nth` helper threads (index ht): robot state HBM ->
 // shared, heading trig, proposed pose and velocity, committed and proposed box
@@ -575,97 +586,25 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
   }
 }
 
-template <int NR>
-__global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant__ KParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-  const int NW = p.NW;              // worker threads of the SENSE phase
-  const int NHT = NT - NW;          // helper threads (>= 32)
-  const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
-  const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
-  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h);
-  float4* const gtab = (float4*)(smem + L.gtab);
-  uint16_t* const gidx = (uint16_t*)(smem + L.gidx);
-  int2* const gcnt = (int2*)(smem + L.gcnt);
-  GroupCull* const gcull = (GroupCull*)(smem + L.gcull);
-  double2* const org = (double2*)(smem + L.org);
-  ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
-  Strip* const strips = (Strip*)(smem + L.strips);
-  double2* const camcs = (double2*)(smem + L.camcs);
-  uint32_t* const rowsky = (uint32_t*)(smem + L.rowsky);
-  uint32_t* const rowgnd = (uint32_t*)(smem + L.rowgnd);
-  uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
-  volatile int* const sched = (volatile int*)(smem + L.sched);
-  const int strips_per_col = 4 * (R - 1);
-  const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
-  const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
 
-  // ---- prologue: barriers, TMA of the first tile, camera tables, PREP of the first tile
-  if (tid == 0) {
-    mbar_init(smem_u32(&mbar[0]), 1);
-    mbar_init(smem_u32(&mbar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int t0 = (int)atomicAdd(&p.sched[0], 1u);
-    sched[0] = t0;
-    if (t0 < p.n_tiles) {
-      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
-      mbar_expect_tx(smem_u32(&mbar[0]), nw * world_bytes);
-      tma_bulk_g2s(smem_u32(smem + L.raw[0]), p.seg + (size_t)w0 * 5 * SC, nw * world_bytes, smem_u32(&mbar[0]));
-    }
-  }
-  for (int i = tid; i < p.n_camera * p.cam_w; i += NT) camcs[i] = p.cam_cs[i];
-  for (int i = tid; i < p.cam_h; i += NT) {
-    rowsky[i] = p.row_sky[i];
-    rowgnd[i] = p.row_gnd[i];
-  }
-  __syncthreads();
-  {
-    const int t0 = sched[0];
-    if (t0 < p.n_tiles) {
-      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
-      mbar_wait(smem_u32(&mbar[0]), 0);
-      prepare_tile(p, w0, nw, tid, NT, do_move, (const uint32_t*)(smem + L.raw[0]), (float4*)(smem + L.segtab[0]),
-                   (double*)(smem + L.ws[0]), (int4*)(smem + L.cflag[0]), (int2*)(smem + L.meta[0]));
-    }
-  }
-  __syncthreads();
-
-  // paint mapping: worker thread -> (picture slot, row slot, column quad)
-  const int pQ = max(p.cam_w >> 2, 1);
-  const int p_q = tid % pQ, p_rest = tid / pQ, p_RS = p.paint_rs;
-  const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQ) / p_RS;
-
-  int it = 0;
-  for (int tile = sched[0]; tile < p.n_tiles; ++it) {
-    const int buf = it & 1;
-    const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
-    const uint32_t* const rawb = (const uint32_t*)(smem + L.raw[buf]);
-    float4* const segtab = (float4*)(smem + L.segtab[buf]);
-    double* const wsb = (double*)(smem + L.ws[buf]);
-    int4* const cflag = (int4*)(smem + L.cflag[buf]);
-    const int2* const meta = (const int2*)(smem + L.meta[buf]);
-    // fetch the next tile index and start its TMA into the other buffer (free
-    // since the barrier that ended the previous iteration)
-    if (tid == 0) {
-      const int tn = (int)atomicAdd(&p.sched[0], 1u);
-      sched[1 + (buf ^ 1)] = tn;
-      if (tn < p.n_tiles) {
-        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-        mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
-        tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
-                     smem_u32(&mbar[buf ^ 1]));
-      }
-    }
-    // every thread observes the phase of this tile's wall store itself before reading it
-    mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
-
-    if (do_move) {
-      // ---------------- phase 2: COLLIDE ---------------------------------------------
-      // walls: GS threads per (world, robot) stride over its segments.  FP32 disc cull
-      // (distance of the proposed centre to the segment vs the box circumradius plus a
-      // margin far above FP32 error), then the exact FP64 4-edge test.
+// Robot.step of one tile by the helper team (thread ht of nth): PREP, then the
+// collision tests, then commit / stall and everything that hangs off the final pose.
+__device__ __forceinline__ void robot_step_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
+                                                bool do_rays, const uint32_t* __restrict__ rawb,
+                                                float4* __restrict__ segtab, double* __restrict__ wsb,
+                                                int4* __restrict__ cflag, int2* __restrict__ meta,
+                                                double2* __restrict__ org, GroupCull* __restrict__ gcull) {
+  const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
+  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta);
+  team_sync(2, nth);
+  if (do_move) {
+    // ---------------- COLLIDE ------------------------------------------------------
+    // walls: GS threads per (world, robot) stride over its segments.  FP32 disc cull
+    // (distance of the proposed centre to the segment vs the box circumradius plus a
+    // margin far above FP32 error), an FP32 classification of the 4 edges, then the
+    // exact FP64 4-edge test for what is not a certain miss.
       {
-        const int GS = p.GS, gi = tid / GS, gl = tid - gi * GS, ngrp = NT / GS;
+        const int GS = min(p.GS, nth), gi = ht / GS, gl = ht - gi * GS, ngrp = nth / GS;
         if (gi < ngrp) {
           for (int i = gi; i < nw * R; i += ngrp) {
             const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
@@ -728,11 +667,11 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
           }
         }
       }
-      // robots: proposal i against the committed box of o (pair_old) and, for o < i,
-      // against the proposal of o (pair_new): Robot.step's list order becomes masks
+    // robots: proposal i against the committed box of o (pair_old) and, for o < i,
+    // against the proposal of o (pair_new): Robot.step's list order becomes masks
       if (R > 1) {
         const int per_world = R * R * 2;
-        for (int i = tid; i < nw * per_world; i += NT) {
+        for (int i = ht; i < nw * per_world; i += nth) {
           const int wl = (int)fdiv(i, p.dPair), k = i - wl * per_world;
           const int ri = (int)fdiv(k >> 1, p.dR), ro = (k >> 1) - ri * R, v = k & 1;
           if (ro == ri || (v && ro > ri)) continue;
@@ -758,15 +697,14 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
           if (hit) atomicOr(v ? &cflag[wl * R + ri].z : &cflag[wl * R + ri].y, 1 << ro);
         }
       }
-      __syncthreads();
-    }
-
-    // ---------------- phase 3: COMMIT ----------------------------------------------
-    // thread per (world, robot): replay the list order on the masks, commit or stall,
-    // then publish everything that hangs off the final pose: the box as FP32 search
-    // segments and the origins of the robot's ray groups.  (During this phase nobody
-    // reads DBOX / POSE / RCS of another robot: the replay only reads the masks.)
-    for (int i = tid; i < nw * R; i += NT) {
+    team_sync(2, nth);
+  }
+  // ---------------- COMMIT ---------------------------------------------------------
+  // thread per (world, robot): replay the list order on the masks, commit or stall,
+  // then publish everything that hangs off the final pose: the box as FP32 search
+  // segments and the origins / cones of the robot's ray groups.  (During this phase
+  // nobody reads DBOX / POSE / RCS of another robot: the replay only reads the masks.)
+    for (int i = ht; i < nw * R; i += nth) {
       const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
       double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
       if (do_move) {
@@ -800,7 +738,7 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
         }
         p.stalled[(size_t)w * R + r] = (uint8_t)(hit ? 1 : 0);
       }
-      if (do_sense || do_cam) {
+      if (do_rays) {
         const double* box = wsr + BRS_WS_DBOX;
         float4* dst = segtab + (size_t)wl * nvis + meta[wl].x + 4 * r;
 #pragma unroll
@@ -827,10 +765,109 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
         }
       }
     }
-    __syncthreads();
+}
 
-    if (do_sense || do_cam) {
-      // ---------------- phase 4: TABLE -------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int NW = p.NW;              // worker threads
+  const int NHT = NT - NW;          // helper team (>= 32)
+  const bool is_helper = tid >= NW;
+  const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
+  const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
+  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h);
+  float4* const gtab = (float4*)(smem + L.gtab);
+  uint16_t* const gidx = (uint16_t*)(smem + L.gidx);
+  int2* const gcnt = (int2*)(smem + L.gcnt);
+  ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
+  Strip* const strips = (Strip*)(smem + L.strips);
+  double2* const camcs = (double2*)(smem + L.camcs);
+  uint32_t* const rowsky = (uint32_t*)(smem + L.rowsky);
+  uint32_t* const rowgnd = (uint32_t*)(smem + L.rowgnd);
+  uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
+  volatile int* const sched = (volatile int*)(smem + L.sched);
+  const int strips_per_col = 4 * (R - 1);
+  const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
+  const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
+  const bool do_rays = do_sense || do_cam;
+
+  // ---- prologue: barriers, camera tables; the helper team schedules, loads and steps tile 0
+  if (tid == NW) {
+    mbar_init(smem_u32(&mbar[0]), 1);
+    mbar_init(smem_u32(&mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int t0 = (int)atomicAdd(&p.sched[0], 1u);
+    sched[0] = t0;
+    if (t0 < p.n_tiles) {
+      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
+      mbar_expect_tx(smem_u32(&mbar[0]), nw * world_bytes);
+      tma_bulk_g2s(smem_u32(smem + L.raw[0]), p.seg + (size_t)w0 * 5 * SC, nw * world_bytes, smem_u32(&mbar[0]));
+    }
+  }
+  for (int i = tid; i < p.n_camera * p.cam_w; i += NT) camcs[i] = p.cam_cs[i];
+  for (int i = tid; i < p.cam_h; i += NT) {
+    rowsky[i] = p.row_sky[i];
+    rowgnd[i] = p.row_gnd[i];
+  }
+  __syncthreads();
+  if (is_helper) {
+    const int t0 = sched[0];
+    if (t0 < p.n_tiles) {
+      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
+      mbar_wait(smem_u32(&mbar[0]), 0);
+      robot_step_tile(p, w0, nw, tid - NW, NHT, do_move, do_rays, (const uint32_t*)(smem + L.raw[0]),
+                      (float4*)(smem + L.segtab[0]), (double*)(smem + L.ws[0]), (int4*)(smem + L.cflag[0]),
+                      (int2*)(smem + L.meta[0]), (double2*)(smem + L.org[0]), (GroupCull*)(smem + L.gcull[0]));
+    }
+  }
+  __syncthreads();
+
+  // paint mapping: worker thread -> (picture slot, row slot, column quad)
+  const int pQ = max(p.cam_w >> 2, 1);
+  const int p_q = tid % pQ, p_rest = tid / pQ, p_RS = p.paint_rs;
+  const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQ) / p_RS;
+
+  int it = 0;
+  for (int tile = sched[0]; tile < p.n_tiles; ++it) {
+    const int buf = it & 1;
+    const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
+    if (is_helper) {
+      // ================= helper team: Robot.step of the NEXT tile =====================
+      if (tid == NW) {
+        // next tile index + TMA of its wall store into the other buffer (free since the
+        // barrier that ended the previous iteration)
+        const int tn = (int)atomicAdd(&p.sched[0], 1u);
+        sched[1 + (buf ^ 1)] = tn;
+        if (tn < p.n_tiles) {
+          const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
+          mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
+          tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
+                       smem_u32(&mbar[buf ^ 1]));
+        }
+      }
+      team_sync(2, NHT);
+      const int tn = sched[1 + (buf ^ 1)];
+      if (tn < p.n_tiles) {
+        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
+        mbar_wait(smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
+        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, (const uint32_t*)(smem + L.raw[buf ^ 1]),
+                        (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
+                        (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
+                        (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]));
+      }
+    } else if (do_rays) {
+      // ================= workers: sensors and pictures of THIS tile ====================
+      const uint32_t* const rawb = (const uint32_t*)(smem + L.raw[buf]);
+      const float4* const segtab = (const float4*)(smem + L.segtab[buf]);
+      const double* const wsb = (const double*)(smem + L.ws[buf]);
+      const int2* const meta = (const int2*)(smem + L.meta[buf]);
+      const double2* const org = (const double2*)(smem + L.org[buf]);
+      const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
+      // every thread observes the phase of this tile's wall store itself before reading it
+      mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+
+      // ---------------- TABLE ------------------------------------------------------------
       // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,
       // na = ex*dy - ey*dx.  Entries no ray of the group can hit are dropped: the own
       // robot's edges, degenerate ones (origin on the wall's line), walls whose line is
@@ -840,7 +877,7 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
       // entries and ties still resolve as in the reference.
       if (NG > 0) {
         const int per_world = NG * nvis;
-        for (int i = tid; i < nw * per_world; i += NT) {
+        for (int i = tid; i < nw * per_world; i += NW) {
           const int wl = (int)fdiv(i, p.dTab), k = i - wl * per_world;
           const int g = (int)fdiv(k, p.dNvis), j = k - g * nvis;
           const int S = meta[wl].x, nv = S + 4 * R;
@@ -867,10 +904,10 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
           }
           gtab[(size_t)wl * per_world + k] = t;
         }
-        __syncthreads();
+        team_sync(1, NW);
         // order-preserving in-place compaction: position <= index, chunks ascend
         {
-          const int warp = tid >> 5, nwarp = NT >> 5;
+          const int warp = tid >> 5, nwarp = NW >> 5;
           for (int pg = warp; pg < nw * NG; pg += nwarp) {
             const int wl = (int)fdiv(pg, p.dNG);
             const int S = meta[wl].x, nv = S + 4 * R;
@@ -896,21 +933,10 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
             if (lane == 0) gcnt[pg] = make_int2(cw, base);
           }
         }
-        __syncthreads();
+        team_sync(1, NW);
       }
-    }
 
-    // ---------------- phase 5: SENSE (workers) + PREP of the next tile (helpers) ----------
-    if (tid >= NW) {
-      const int tn = sched[1 + (buf ^ 1)];  // written before the barriers above
-      if (tn < p.n_tiles) {
-        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-        mbar_wait(smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
-        prepare_tile(p, wn, nn, tid - NW, NHT, do_move, (const uint32_t*)(smem + L.raw[buf ^ 1]),
-                     (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
-                     (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]));
-      }
-    } else if (do_sense || do_cam) {
+      // ---------------- SENSE --------------------------------------------------------------
       // 5a. group path: camera column blocks, then grouped range sensors
       {
         const int SL = p.SLG, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
@@ -1085,11 +1111,10 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
           }
         }
       }
-    }
 
-    // ---------------- phase 6: PAINT ---------------------------------------------------
-    if (do_cam) {
-      __syncthreads();
+      // ---------------- PAINT ----------------------------------------------------------------
+      if (do_cam) {
+        team_sync(1, NW);
       const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
       const int nimg = nw * p.n_camera;
       uint4* const out0 = (uint4*)(p.cam_out + (size_t)w0 * p.n_camera * (size_t)H * W * 4);
@@ -1104,12 +1129,13 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
       } else {
         // picture wider than 4 x threads: several quads per thread
         for (int im = 0; im < nimg; ++im)
-          for (int q = tid; q < Q; q += NT)
+          for (int q = tid; q < Q; q += NW)
             paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
                        strips_per_col, rowsky, rowgnd, q, Q, 0, 1, H);
       }
+      }
     }
-    __syncthreads();  // tile done: its buffers are free, the next tile is prepared
+    __syncthreads();  // the teams meet: this tile is done, the next one is stepped
     tile = sched[1 + (buf ^ 1)];
   }
 
