@@ -51,11 +51,14 @@ struct brs_engine {
   double2* d_camcs = nullptr;
   uint32_t* d_rowsky = nullptr;
   uint32_t* d_rowgnd = nullptr;
+  int flat_rows = 1;
   unsigned int* d_sched = nullptr;
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
   int gtasks = 0, dtasks = 0;
+  bool big = false;
+  const void* kfn = nullptr;
 };
 
 static int pow2floor(int x) {
@@ -327,6 +330,9 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     rowgnd[j] = pack_rgb(cfg->ground_rgb[0] + cfg->ground_grad[0] * dist, cfg->ground_rgb[1] + cfg->ground_grad[1] * dist,
                          cfg->ground_rgb[2] + cfg->ground_grad[2] * dist);
   }
+  e->flat_rows = 1;
+  for (int j = 1; j < e->cam_h; ++j)
+    if (rowsky[j] != rowsky[0] || rowgnd[j] != rowgnd[0]) e->flat_rows = 0;
   int rc;
   if ((rc = to_device(&e->d_robots, rdev)) || (rc = to_device(&e->d_ranges, gdev)) ||
       (rc = to_device(&e->d_cameras, cdev)) || (rc = to_device(&e->d_lights, ldev)) ||
@@ -383,22 +389,27 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->gtasks = gtasks;
   e->dtasks = dtasks;
   const int tasks = std::max(gtasks + dtasks, 1);
-  e->NW = env_int("BRS_NW", 256);
-  if (e->NW != 64 && e->NW != 128 && e->NW != 256) e->NW = 256;
   auto smem_for = [&](int tw) { return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h).total; };
-  const int budget = env_int("BRS_SMEM_BUDGET", 72 * 1024);
-  // as many worlds per tile as the budget allows (amortises barriers, fills the lanes
-  // of the per-robot phases), but keep >= ~8 tiles per SM for the dynamic scheduler
+  // small shape (128 workers, 4 CTAs/SM) unless one world's footprint leaves room for <= 2 CTAs
+  const int smem_sm = (int)prop.sharedMemPerMultiprocessor - 4096;
+  e->big = smem_for(1) > smem_sm / 3;
+  e->big = env_int("BRS_BIG", e->big ? 1 : 0) != 0;
+  e->NW = env_int("BRS_NW", e->big ? 256 : 128);
+  if (e->NW != 64 && e->NW != 128 && e->NW != 192 && e->NW != 256) e->NW = e->big ? 256 : 128;
+  if (!e->big && e->NW > 128) e->NW = 128;
+  const int budget = env_int("BRS_SMEM_BUDGET", e->big ? smem_sm / BRS_BIG_CTAS : smem_sm / BRS_SMALL_CTAS);
+  // worlds per tile: as many as the budget allows (amortises barriers, fills the lanes of
+  // the per-robot phases) while keeping >= ~8 tiles per SM for the dynamic scheduler; among
+  // those prefer the count whose ray tasks fill whole passes of the workers
   int tw_max = std::min(64, std::max(1, cfg->n_worlds / (e->sm_count * 8)));
   while (tw_max > 1 && smem_for(tw_max) > budget) --tw_max;
-  // among tw <= tw_max prefer the one whose ray tasks fill whole passes of the workers
   int tw = tw_max;
   {
     double best = -1;
-    for (int t = tw_max; t >= std::max(1, tw_max / 2); --t) {
+    for (int t = tw_max; t >= 1; --t) {
       const int n = t * tasks, passes = (n + e->NW - 1) / e->NW;
       const double eff = (double)n / ((double)passes * e->NW);
-      if (eff > best + 0.02) { best = eff; tw = t; }
+      if (eff > best + 0.05) { best = eff; tw = t; }
     }
   }
   tw = env_int("BRS_TW", tw);
@@ -417,11 +428,14 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->SLD = dtasks ? std::min(32, pow2floor(std::max(e->NW / (dtasks * tw), 1))) : 1;
   {
     const int Q = std::max(e->cam_w / 4, 1);
-    const int slots = std::max(e->NW / Q, 1);
+    const int slots = std::max(e->NW / std::min(Q, e->NW), 1);
     const int nislot = std::max(1, std::min(tw * std::max(cfg->n_camera, 1), slots));
     e->paint_rs = std::max(1, slots / nislot);
   }
-  const void* kfn = e->NR == 4 ? (const void*)brs_step_kernel<4> : e->NR == 2 ? (const void*)brs_step_kernel<2> : (const void*)brs_step_kernel<1>;
+  if (e->NR == 4) e->NR = 2;  // (4 columns per thread measured slower than 2)
+  const void* kfn = e->big ? (e->NR == 2 ? (const void*)brs_step_kernel<2, true> : (const void*)brs_step_kernel<1, true>)
+                           : (e->NR == 2 ? (const void*)brs_step_kernel<2, false> : (const void*)brs_step_kernel<1, false>);
+  e->kfn = kfn;
   cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem);
   int nb = 0;
   if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, e->T, e->smem);
@@ -515,6 +529,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.cam_w = e->cam_w; p.cam_h = e->cam_h;
   p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
   p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.paint_rs = e->paint_rs;
+  p.flat_rows = e->flat_rows;
   p.NW = e->NW; p.NH = e->NH;
   {
     const int R = c.n_robots, nvis = c.seg_cap + 4 * R;
@@ -547,12 +562,10 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.groups = e->d_groups; p.gr_idx = e->d_gr_idx; p.dr_idx = e->d_dr_idx;
   p.cam_cs = e->d_camcs; p.row_sky = e->d_rowsky; p.row_gnd = e->d_rowgnd;
   p.sched = e->d_sched;
-  if (e->NR == 4)
-    brs_step_kernel<4><<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
-  else if (e->NR == 2)
-    brs_step_kernel<2><<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
-  else
-    brs_step_kernel<1><<<e->grid, e->T, e->smem, (cudaStream_t)stream>>>(p);
+  {
+    void* args[] = {(void*)&p};
+    CK(cudaLaunchKernel(e->kfn, dim3(e->grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
+  }
   CK(cudaGetLastError());
   return BRS_OK;
 }
@@ -607,6 +620,17 @@ extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem
   if (ctas) *ctas = e->grid;
   if (smem_bytes) *smem_bytes = e->smem;
   if (sm_count) *sm_count = e->sm_count;
+  return BRS_OK;
+}
+
+extern "C" int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* workers, int* cols_per_thread,
+                             int* n_groups) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_tile_info: null engine");
+  if (worlds_per_tile) *worlds_per_tile = e->TW;
+  if (n_tiles) *n_tiles = e->n_tiles;
+  if (workers) *workers = e->NW;
+  if (cols_per_thread) *cols_per_thread = e->NR;
+  if (n_groups) *n_groups = e->n_group;
   return BRS_OK;
 }
 

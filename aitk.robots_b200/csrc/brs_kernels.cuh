@@ -104,6 +104,7 @@ struct KParams {
   int SLG, SLD;      // lanes per ray task: group path, direct path (powers of two <= 32)
   int n_gr, n_dr;    // range sensors on the group path / on the direct path
   int paint_rs;      // row slots of the paint phase
+  int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
   int NH;            // helper warps: prepare the next tile during the SENSE phase
   FastDiv dR, dSC, dTab, dNvis, dPair, dGT, dDT, dCpb, dNG;
@@ -196,6 +197,27 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
 #ifdef __CUDACC__
 
 #define BRS_PI_OVER_2 1.5707963267948966
+
+// inlining policy of the heavy FP64 helpers (code size vs call overhead), tunable at build time
+#ifndef BRS_INL_REFINE
+#define BRS_INL_REFINE __forceinline__
+#endif
+#ifndef BRS_INL_CAMCOL
+#define BRS_INL_CAMCOL __forceinline__
+#endif
+#ifndef BRS_INL_DIRECT
+#define BRS_INL_DIRECT __forceinline__
+#endif
+#ifndef BRS_INL_ROBOT
+#define BRS_INL_ROBOT __forceinline__
+#endif
+// two launch shapes: 128 workers + 32 helpers at 4 CTAs/SM (<= 96 registers; the measured
+// optimum for worlds that fit several CTAs per SM), or 256 + 32 at 2 CTAs/SM for worlds
+// whose shared-memory footprint leaves room for one or two CTAs only
+#define BRS_SMALL_THREADS 160
+#define BRS_SMALL_CTAS 4
+#define BRS_BIG_THREADS 288
+#define BRS_BIG_CTAS 2
 
 // ---- exact (never contracted) float64 helpers --------------------------------
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
@@ -328,7 +350,7 @@ __device__ __forceinline__ void group_max(uint32_t& key, int& idx, int SL, uint3
 // / inf parameters compare above BRS_KEY_NOHIT), smaller is nearer.
 #define BRS_KEY_NOHIT 0x3F800001u  // just above 1.0f: parameters <= 1 are hits
 template <bool SL1>
-__device__ __forceinline__ void search_direct(const float4* __restrict__ segtab, int j0, int j1, int g, int SLrt,
+__device__ BRS_INL_DIRECT void search_direct(const float4* __restrict__ segtab, int j0, int j1, int g, int SLrt,
                                               float ox, float oy, float rx, float ry, uint32_t& key, int& idx) {
   const int SL = SL1 ? 1 : SLrt;
 #pragma unroll 4
@@ -379,7 +401,7 @@ __device__ __forceinline__ void seg64(const uint32_t* raw, int SC, int S, const 
 
 // float64 distance of the hit of ray (x1,y1)->(x2,y2) on segment j, computed
 // like cast_ray: pos = intersect_hit(...), dist = distance(pos, origin)
-__device__ __forceinline__ double refine64(const uint32_t* raw, int SC, int S, const double* ws, int j, double x1,
+__device__ BRS_INL_REFINE double refine64(const uint32_t* raw, int SC, int S, const double* ws, int j, double x1,
                                            double y1, double x2, double y2) {
   double x3, y3, x4, y4;
   seg64(raw, SC, S, ws, j, x3, y3, x4, y4);
@@ -414,41 +436,52 @@ __device__ __forceinline__ void mount_point(const double* wsr, double mx, double
 
 // Paint rows r0, r0+rstep, ... of the 4 columns of quad q of one picture
 // (upstream Camera.take_picture: sky above, shaded wall, ground below, then the
-// strips of other robots back to front).
+// strips of other robots back to front).  The common case -- flat sky and ground
+// colours, every column hit a wall, no robot in sight -- is a tight loop of two
+// compares and two selects per pixel; everything else takes the generic loop.
 __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInfo* __restrict__ cinf,
                                            const Strip* __restrict__ strips, int strips_per_col,
                                            const uint32_t* __restrict__ rowsky, const uint32_t* __restrict__ rowgnd,
-                                           int q, int Q, int r0, int rstep, int H) {
+                                           bool flat, int q, int Q, int r0, int rstep, int H) {
   ColInfo ci[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) ci[k] = cinf[4 * q + k];
-  // rare per-quad extras (robot strips, a column without any wall hit) take a slow path
   const bool slow = ((ci[0].n_robot | ci[1].n_robot | ci[2].n_robot | ci[3].n_robot) != 0) ||
-                    ((ci[0].top | ci[1].top | ci[2].top | ci[3].top) < 0);
+                    ((ci[0].top | ci[1].top | ci[2].top | ci[3].top) < 0) || !flat;
   uint4* o = out + (size_t)r0 * Q + q;
   const size_t ostep = (size_t)rstep * Q;
+  if (!slow) {
+    const uint32_t sky = rowsky[0], gnd = rowgnd[0];
 #pragma unroll 4
+    for (int j = r0; j < H; j += rstep, o += ostep) {
+      uint32_t px[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) px[k] = j < ci[k].top ? sky : (j < ci[k].bot ? ci[k].rgba : gnd);
+      __stcs(o, make_uint4(px[0], px[1], px[2], px[3]));
+    }
+    return;
+  }
+#pragma unroll 1
   for (int j = r0; j < H; j += rstep, o += ostep) {
     const uint32_t sky = rowsky[j], gnd = rowgnd[j];
     uint32_t px[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) px[k] = j < ci[k].top ? sky : (j < ci[k].bot ? ci[k].rgba : gnd);
-    if (slow) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (ci[k].top < 0) px[k] = 0u;  // no wall hit: the column keeps the blank RGBA (0,0,0,0)
-        const Strip* st = strips + (size_t)(4 * q + k) * strips_per_col;
-        float best = 3.0e38f;
-        for (int n = 0; n < ci[k].n_robot; ++n) {
-          const Strip sp = st[n];
-          // back-to-front painting == the nearest covering strip wins, the later
-          // one among equally distant strips
-          if (j >= sp.lo && j <= sp.hi && sp.dist <= best) {
-            best = sp.dist;
-            px[k] = sp.rgba;
-          }
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const ColInfo c = cinf[4 * q + k];
+      uint32_t v = j < c.top ? sky : (j < c.bot ? c.rgba : gnd);
+      if (c.top < 0) v = 0u;  // no wall hit: the column keeps the blank RGBA (0,0,0,0)
+      const Strip* st = strips + (size_t)(4 * q + k) * strips_per_col;
+      float best = 3.0e38f;
+      for (int n = 0; n < c.n_robot; ++n) {
+        const Strip sp = st[n];
+        // back-to-front painting == the nearest covering strip wins, the later
+        // one among equally distant strips
+        if (j >= sp.lo && j <= sp.hi && sp.dist <= best) {
+          best = sp.dist;
+          v = sp.rgba;
         }
       }
+      px[k] = v;
     }
     __stcs(o, make_uint4(px[0], px[1], px[2], px[3]));
   }
@@ -456,7 +489,7 @@ __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInf
 
 // Wall column record + robot strips of one camera ray (upstream Camera._update
 // and the per-column part of take_picture).
-__device__ __forceinline__ void camera_column(const KParams& p, const CameraDev& cd, int r, int idx, const uint32_t* raw,
+__device__ BRS_INL_CAMCOL void camera_column(const KParams& p, const CameraDev& cd, int r, int idx, const uint32_t* raw,
                                               int SC, int S, const double* ws, double wsize, double x1, double y1,
                                               double x2, double y2, ColInfo* ci_out, Strip* st) {
   const int R = p.n_robots;
@@ -589,7 +622,7 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
 
 // Robot.step of one tile by the helper team (thread ht of nth): PREP, then the
 // collision tests, then commit / stall and everything that hangs off the final pose.
-__device__ __forceinline__ void robot_step_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
+__device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
                                                 bool do_rays, const uint32_t* __restrict__ rawb,
                                                 float4* __restrict__ segtab, double* __restrict__ wsb,
                                                 int4* __restrict__ cflag, int2* __restrict__ meta,
@@ -767,8 +800,9 @@ __device__ __forceinline__ void robot_step_tile(const KParams& p, int w0, int nw
     }
 }
 
-template <int NR>
-__global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant__ KParams p) {
+template <int NR, bool BIG>
+__global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG ? BRS_BIG_CTAS : BRS_SMALL_CTAS)
+    brs_step_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
   const int NW = p.NW;              // worker threads
@@ -792,18 +826,11 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
   const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
   const bool do_rays = do_sense || do_cam;
 
-  // ---- prologue: barriers, camera tables; the helper team schedules, loads and steps tile 0
+  // ---- prologue: barriers, camera tables
   if (tid == NW) {
     mbar_init(smem_u32(&mbar[0]), 1);
     mbar_init(smem_u32(&mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int t0 = (int)atomicAdd(&p.sched[0], 1u);
-    sched[0] = t0;
-    if (t0 < p.n_tiles) {
-      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
-      mbar_expect_tx(smem_u32(&mbar[0]), nw * world_bytes);
-      tma_bulk_g2s(smem_u32(smem + L.raw[0]), p.seg + (size_t)w0 * 5 * SC, nw * world_bytes, smem_u32(&mbar[0]));
-    }
   }
   for (int i = tid; i < p.n_camera * p.cam_w; i += NT) camcs[i] = p.cam_cs[i];
   for (int i = tid; i < p.cam_h; i += NT) {
@@ -811,25 +838,15 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
     rowgnd[i] = p.row_gnd[i];
   }
   __syncthreads();
-  if (is_helper) {
-    const int t0 = sched[0];
-    if (t0 < p.n_tiles) {
-      const int w0 = t0 * TW, nw = min(TW, p.n_worlds - w0);
-      mbar_wait(smem_u32(&mbar[0]), 0);
-      robot_step_tile(p, w0, nw, tid - NW, NHT, do_move, do_rays, (const uint32_t*)(smem + L.raw[0]),
-                      (float4*)(smem + L.segtab[0]), (double*)(smem + L.ws[0]), (int4*)(smem + L.cflag[0]),
-                      (int2*)(smem + L.meta[0]), (double2*)(smem + L.org[0]), (GroupCull*)(smem + L.gcull[0]));
-    }
-  }
-  __syncthreads();
 
   // paint mapping: worker thread -> (picture slot, row slot, column quad)
-  const int pQ = max(p.cam_w >> 2, 1);
-  const int p_q = tid % pQ, p_rest = tid / pQ, p_RS = p.paint_rs;
-  const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQ) / p_RS;
+  const int pQ = max(p.cam_w >> 2, 1), pQc = min(pQ, NW);  // pictures wider than 4 x NW: several quads per thread
+  const int p_q = tid % pQc, p_rest = tid / pQc, p_RS = p.paint_rs;
+  const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQc) / p_RS;
 
-  int it = 0;
-  for (int tile = sched[0]; tile < p.n_tiles; ++it) {
+  // iteration -1 only lets the helper team step the CTA's first tile
+  int tile = 0;
+  for (int it = -1;; ++it) {
     const int buf = it & 1;
     const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
     if (is_helper) {
@@ -856,7 +873,7 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
                         (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
                         (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]));
       }
-    } else if (do_rays) {
+    } else if (do_rays && it >= 0) {
       // ================= workers: sensors and pictures of THIS tile ====================
       const uint32_t* const rawb = (const uint32_t*)(smem + L.raw[buf]);
       const float4* const segtab = (const float4*)(smem + L.segtab[buf]);
@@ -1118,25 +1135,19 @@ __global__ void __launch_bounds__(288, 3) brs_step_kernel(const __grid_constant_
       const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
       const int nimg = nw * p.n_camera;
       uint4* const out0 = (uint4*)(p.cam_out + (size_t)w0 * p.n_camera * (size_t)H * W * 4);
-      if (NW >= Q) {
-        // worker thread -> (picture slot, row slot, column quad): the 4 column records stay
-        // in registers over the rows, a warp writes whole 128-byte lines per store
-        if (tid < NW && p_islot < p_nislot) {
-          for (int im = p_islot; im < nimg; im += p_nislot)
+      // worker thread -> (picture slot, row slot, column quad): the 4 column records stay
+      // in registers over the rows, a warp writes whole 128-byte lines per store
+      if (p_islot < p_nislot) {
+        for (int im = p_islot; im < nimg; im += p_nislot)
+          for (int q = p_q; q < Q; q += NW)
             paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
-                       strips_per_col, rowsky, rowgnd, p_q, Q, p_rslot, p_RS, H);
-        }
-      } else {
-        // picture wider than 4 x threads: several quads per thread
-        for (int im = 0; im < nimg; ++im)
-          for (int q = tid; q < Q; q += NW)
-            paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
-                       strips_per_col, rowsky, rowgnd, q, Q, 0, 1, H);
+                       strips_per_col, rowsky, rowgnd, p.flat_rows != 0, q, Q, p_rslot, p_RS, H);
       }
       }
     }
     __syncthreads();  // the teams meet: this tile is done, the next one is stepped
     tile = sched[1 + (buf ^ 1)];
+    if (tile >= p.n_tiles) break;
   }
 
   // self-resetting scheduler: the last CTA to leave zeroes both counters for the next launch

@@ -226,7 +226,11 @@ class BatchEngine:
     def launch_info(self):
         t, c, s, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         cabi.check(self._lib.brs_launch_info(self._h, C.byref(t), C.byref(c), C.byref(s), C.byref(m)))
-        return {"threads": t.value, "ctas": c.value, "smem_bytes": s.value, "sm_count": m.value}
+        tw, nt, nw, nr, ng = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        cabi.check(self._lib.brs_tile_info(self._h, C.byref(tw), C.byref(nt), C.byref(nw), C.byref(nr), C.byref(ng)))
+        return {"threads": t.value, "ctas": c.value, "smem_bytes": s.value, "sm_count": m.value,
+                "worlds_per_tile": tw.value, "tiles": nt.value, "workers": nw.value, "cols_per_thread": nr.value,
+                "ray_groups": ng.value}
 
     def synchronize(self, stream=0):
         cabi.check(self._lib.brs_synchronize(self._h, stream))

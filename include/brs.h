@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BRS_ABI_VERSION 1
+#define BRS_ABI_VERSION 2
 #define BRS_MAX_ROBOTS 8 /* robots per world */
 
 typedef enum brs_status {
@@ -179,6 +179,12 @@ int brs_count_tests(brs_engine* e, unsigned flags, void* stream, unsigned long l
 /* Launch geometry chosen for this engine (for reports): threads per CTA,
  * CTAs in the persistent grid, dynamic shared memory bytes. */
 int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem_bytes, int* sm_count);
+
+/* Tiling chosen for this engine (for reports): worlds stepped per CTA pass,
+ * number of tiles, worker threads per CTA (the CTA has `threads` of
+ * brs_launch_info = workers + one helper warp), camera columns per worker
+ * thread, shared-origin ray groups per world. */
+int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* workers, int* cols_per_thread, int* n_groups);
 
 /* FP32 FFMA throughput microbenchmark on the engine's device: runs `iters`
  * dependent-chain FFMA sweeps on every SM and returns TFLOP/s (2 flop / FFMA)
