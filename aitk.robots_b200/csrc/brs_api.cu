@@ -282,8 +282,9 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       for (int i = 0; i < cfg->n_camera; ++i)
         if (cdev[i].group == (int)k) {
           const brs_camera_desc& d = e->cameras[i];
-          ang.push_back(-d.fov / 2);
-          ang.push_back((double)(d.width - 1) / (double)d.width * d.fov - d.fov / 2);
+          // every column direction: the fan is contiguous, its two ends alone would let a
+          // wide fan (> 180 deg) pass for the short arc through the robot's back
+          for (int q = 0; q < d.width; ++q) ang.push_back((double)q / (double)d.width * d.fov - d.fov / 2);
           range = std::fmax(range, d.max_range);
         }
       for (int i = 0; i < cfg->n_range; ++i)

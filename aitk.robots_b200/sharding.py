@@ -7,8 +7,10 @@ this rank's slice of the gather buffer (brs_bind_output), so no staging copy
 precedes the collective (NCCL in-place all-gather).
 """
 
-import torch
-import torch.distributed as dist
+def _dist():
+    import torch.distributed as dist  # lazy: the CPU baseline workers never touch torch
+
+    return dist
 
 
 def partition(n_worlds, world_size, rank):
@@ -21,6 +23,9 @@ def partition(n_worlds, world_size, rank):
 
 def all_gather_worlds(local, counts=None, group=None):
     """All-gather per-rank [n_r, ...] tensors along dim 0 (works on gloo and nccl)."""
+    import torch
+
+    dist = _dist()
     ws = dist.get_world_size(group)
     if counts is None or len(set(counts)) == 1:
         out = local.new_empty((local.shape[0] * ws,) + tuple(local.shape[1:]))
@@ -45,8 +50,11 @@ class ShardedWorlds:
     """
 
     def __init__(self, scene_fn, n_worlds, device=None, group=None):
+        import torch
+
         from .engine import BatchEngine
 
+        dist = _dist()
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -63,6 +71,8 @@ class ShardedWorlds:
     def gather_buffer(self, name):
         """Allocate the global observation tensor and make the kernels write this
         rank's slice of it directly (equal shard sizes only)."""
+        import torch
+
         if len(set(self.counts)) != 1:
             raise ValueError("in-place gather needs equal shards; use all_gather()")
         local = self.engine.tensor(name)
@@ -77,7 +87,7 @@ class ShardedWorlds:
         if name in self._gather:
             full, mine = self._gather[name]
             if self.world_size > 1:
-                dist.all_gather_into_tensor(full, mine, group=self.group)  # in place: mine is full's slice
+                _dist().all_gather_into_tensor(full, mine, group=self.group)  # in place: mine is full's slice
             return full
         local = self.engine.tensor(name)
         if self.world_size == 1:

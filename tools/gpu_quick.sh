@@ -18,7 +18,7 @@ for f in sorted(glob.glob("$OUT/bench_*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         r=d["roofline"]
-        print(f.split("bench_")[1][:-5], "ws/s=%.3g tests/s=%.3g ms=%.4f hbm=%.3f fp32=%.4f e2e=%.3g"%(d["value"],d["ray_segment_tests_per_sec"],d["ms_per_step"],r["frac"],r["fp32"]["frac_measured"] or 0,d["e2e"]["value"]), d["config"]["launch"])
+        print(f.split("bench_")[1][:-5], "ws/s=%.3g tests/s=%.3g ms=%.4f hbm=%.3f fp32=%.4f e2e=%.3g"%(d["value"],d["ray_segment_tests_per_sec"],d["ms_per_step"],r["hbm"]["frac"],r["fp32"]["frac"],d["e2e"]["value"]), d["config"]["launch"])
     except Exception as e:
         print(f, "ERR", e, open(f.replace('.json','.err')).read()[-400:])
 PY

@@ -13,7 +13,7 @@ import json
 try:
     d=json.loads(open("$OUT/sw_${cfg}_$name.json").read().strip().splitlines()[-1])
     r=d["roofline"]
-    print("$cfg [$envs]", "ms=%.4f hbm=%.3f fp32=%.4f"%(d["ms_per_step"],r["frac"],r["fp32"]["frac_measured"] or 0), d["config"]["launch"])
+    print("$cfg [$envs]", "ms=%.4f hbm=%.3f fp32=%.4f"%(d["ms_per_step"],r["hbm"]["frac"],r["fp32"]["frac"]), d["config"]["launch"])
 except Exception as e:
     print("$cfg [$envs] ERR", e, open("$OUT/sw_${cfg}_$name.err").read()[-300:])
 PY

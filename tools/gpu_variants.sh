@@ -13,7 +13,7 @@ for spec in "$@"; do
 import json
 try:
     d=json.loads(open("$f").read().strip().splitlines()[-1]); r=d["roofline"]
-    print("%-10s %-8s [%s] ms=%.4f hbm=%.3f fp32=%.4f"%("$cfg","$v","$envs",d["ms_per_step"],r["frac"],r["fp32"]["frac_measured"] or 0), d["config"]["launch"])
+    print("%-10s %-8s [%s] ms=%.4f hbm=%.3f fp32=%.4f"%("$cfg","$v","$envs",d["ms_per_step"],r["hbm"]["frac"],r["fp32"]["frac"]), d["config"]["launch"])
 except Exception as e:
     print("$cfg $v [$envs] ERR", e, open("${f%.json}.err").read()[-300:])
 PY
