@@ -9,7 +9,7 @@ contains a dot; see ../aitk_robots_b200.py).
 """
 
 from . import _cabi  # noqa: F401
-from .engine import BatchEngine, measure_fp32_peak  # noqa: F401
+from .engine import BatchEngine, measure_fp32_peak, measure_write_bw  # noqa: F401
 from .scenes import (  # noqa: F401
     CameraSpec,
     LightSpec,

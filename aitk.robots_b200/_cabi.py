@@ -132,6 +132,7 @@ SYMBOLS = [
     ("brs_count_tests", C.c_int, [_P, C.c_uint, _P, C.POINTER(C.c_ulonglong)]),
     ("brs_launch_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("brs_tile_info", C.c_int, [_P] + [C.POINTER(C.c_int)] * 5),
+    ("brs_measure_write_bw", C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("brs_measure_fp32_peak", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 

@@ -400,9 +400,9 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   if (!e->big && e->NW > 128) e->NW = 128;
   const int budget = env_int("BRS_SMEM_BUDGET", e->big ? smem_sm / BRS_BIG_CTAS : smem_sm / BRS_SMALL_CTAS);
   // worlds per tile: as many as the budget allows (amortises barriers, fills the lanes of
-  // the per-robot phases) while keeping >= ~8 tiles per SM for the dynamic scheduler; among
+  // the per-robot phases) while keeping >= ~6 tiles per resident CTA for the dynamic scheduler; among
   // those prefer the count whose ray tasks fill whole passes of the workers
-  int tw_max = std::min(64, std::max(1, cfg->n_worlds / (e->sm_count * 8)));
+  int tw_max = std::min(64, std::max(1, cfg->n_worlds / (e->sm_count * (e->big ? BRS_BIG_CTAS : BRS_SMALL_CTAS) * 6)));
   while (tw_max > 1 && smem_for(tw_max) > budget) --tw_max;
   int tw = tw_max;
   {
@@ -663,6 +663,39 @@ extern "C" int brs_measure_fp32_peak(int device, int iters, double* tflops, doub
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     *sm_clock_mhz = khz / 1000.0;
   }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  return BRS_OK;
+}
+
+extern "C" int brs_measure_write_bw(int device, size_t bytes, int mode, int reps, double* gbs) {
+  if (!gbs || bytes < 4096 || reps < 1) return fail(BRS_ERR_INVALID, "brs_measure_write_bw: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRS_ERR_NO_DEVICE, "brs_measure_write_bw: no such CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  uint4* d = nullptr;
+  CK(cudaMalloc((void**)&d, bytes));
+  const size_t n16 = bytes / 16;
+  const int blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  brs_fill_kernel<<<blocks, 256>>>(d, n16, mode);  // warm-up
+  double best = 0;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(a));
+    brs_fill_kernel<<<blocks, 256>>>(d, n16, mode);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    best = std::max(best, (double)(n16 * 16) / (ms * 1e-3) / 1e9);
+  }
+  *gbs = best;
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   cudaFree(d);

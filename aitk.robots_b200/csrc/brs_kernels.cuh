@@ -42,7 +42,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef BRS_PAINT_UNROLL
+#define BRS_PAINT_UNROLL 4  // rows in flight per thread in the PAINT fast path
+#endif
+
 namespace brs {
+
+constexpr int kPaintUnroll = BRS_PAINT_UNROLL;
 
 // ---- device-side descriptors (host-precomputed from the public brs_*_desc) ----
 struct RobotDev {
@@ -452,7 +458,7 @@ __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInf
   const size_t ostep = (size_t)rstep * Q;
   if (!slow) {
     const uint32_t sky = rowsky[0], gnd = rowgnd[0];
-#pragma unroll 4
+#pragma unroll kPaintUnroll
     for (int j = r0; j < H; j += rstep, o += ostep) {
       uint32_t px[4];
 #pragma unroll
@@ -1177,6 +1183,21 @@ __global__ void __launch_bounds__(1024) brs_ffma_kernel(float* out, int iters, f
   }
   const float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
   if (s == 123.456f) out[0] = s;  // keeps the chain alive, practically never taken
+}
+
+// ------------------------------------------------------------------------------
+// HBM write-bandwidth microbenchmark: every thread streams 16-byte stores over a
+// buffer, grid-stride (what PAINT does, without the work).  mode 0: st.global.cs
+// (the kernel's policy), 1: default policy.  Roofline context for picture-bound worlds.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) brs_fill_kernel(uint4* out, size_t n16, int mode) {
+  const uint4 v = make_uint4(threadIdx.x, blockIdx.x, 0xff00ff00u, 0xffffffffu);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    if (mode == 0)
+      __stcs(out + i, v);
+    else
+      out[i] = v;
+  }
 }
 
 #endif  // __CUDACC__

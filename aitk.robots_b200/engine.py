@@ -241,3 +241,11 @@ def measure_fp32_peak(device=0, iters=4096):
     tf, mhz = C.c_double(), C.c_double()
     cabi.check(lib.brs_measure_fp32_peak(int(device), int(iters), C.byref(tf), C.byref(mhz)))
     return tf.value, mhz.value
+
+
+def measure_write_bw(device=0, nbytes=512 << 20, mode=0, reps=5):
+    """GB/s of plain streaming 16-byte stores (the PAINT phase without its work)."""
+    lib = cabi.load()
+    g = C.c_double()
+    cabi.check(lib.brs_measure_write_bw(int(device), int(nbytes), int(mode), int(reps), C.byref(g)))
+    return g.value

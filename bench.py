@@ -313,21 +313,27 @@ def main():
     # ---- optional observation all-gather (the only collective of the path) ---------
     gather = None
     if args.gather and world_size > 1:
-        t_range = eng.tensor("range")
-        full = torch.empty((B * world_size,) + tuple(t_range.shape[1:]), dtype=t_range.dtype, device=t_range.device)
+        # the kernels write this rank's slice of the gather buffer directly (brs_bind_output),
+        # the all-gather is in place: no staging copy precedes the collective
+        name = "camera" if eng.n_camera else "range"
+        local = eng.tensor(name)
+        full = torch.empty((B * world_size,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        mine = full[rank * B:(rank + 1) * B]
+        eng.bind_output(name, mine)
         for _ in range(3):
             eng.step(flags=flags, stream=sh)
-            dist.all_gather_into_tensor(full, t_range)
+            dist.all_gather_into_tensor(full, mine)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
         for _ in range(args.steps):
             eng.step(flags=flags, stream=sh)
-            dist.all_gather_into_tensor(full, t_range)
+            dist.all_gather_into_tensor(full, mine)
         g1.record(stream)
         barrier()
-        gather = {"observation": "range", "bytes_per_rank_per_step": int(t_range.numel() * 4),
-                  "ms_per_step": g0.elapsed_time(g1) / args.steps}
+        eng.bind_output(name, None)
+        gather = {"observation": name, "bytes_per_rank_per_step": int(mine.numel() * mine.element_size()),
+                  "ms_per_step_with_gather": g0.elapsed_time(g1) / args.steps, "in_place": True}
 
     # ---- max over ranks ---------------------------------------------------------------
     t = torch.tensor([total_ms, e2e_ms, float(tests_per_step)], dtype=torch.float64, device="cuda")

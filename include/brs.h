@@ -191,6 +191,11 @@ int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* worker
  * timed with CUDA events.  Used only for the roofline denominator. */
 int brs_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz);
 
+/* HBM write-bandwidth microbenchmark on `device`: streams `bytes` of 16-byte stores
+ * (mode 0: st.global.cs as the PAINT phase uses, 1: default cache policy), best of
+ * `reps` launches timed with CUDA events, in GB/s.  Roofline context only. */
+int brs_measure_write_bw(int device, size_t bytes, int mode, int reps, double* gbs);
+
 #ifdef __cplusplus
 }
 #endif
