@@ -531,6 +531,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
   p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.paint_rs = e->paint_rs;
   p.flat_rows = e->flat_rows;
+  p.fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
   p.NW = e->NW; p.NH = e->NH;
   {
     const int R = c.n_robots, nvis = c.seg_cap + 4 * R;

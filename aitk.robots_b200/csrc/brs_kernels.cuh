@@ -87,6 +87,8 @@ struct GroupDev {  // rays sharing one origin: robot + mount offset, and what th
 struct __align__(16) GroupCull {  // per (world, group), world frame
   float lo_x, lo_y, hi_x, hi_y, ax_x, ax_y, range2;
   int has_cone;
+  float ox, oy;  // origin rounded to FP32 (search only; refinement uses the float64 origin)
+  float _pad[2];
 };
 
 // n / d for n * d < 2^32 as one multiply-high (host precomputes ceil(2^32 / d))
@@ -110,6 +112,7 @@ struct KParams {
   int SLG, SLD;      // lanes per ray task: group path, direct path (powers of two <= 32)
   int n_gr, n_dr;    // range sensors on the group path / on the direct path
   int paint_rs;      // row slots of the paint phase
+  int fused_table;   // TABLE phase: one warp per (world, group) builds and compacts in one pass
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
   int NH;            // helper warps: prepare the next tile during the SENSE phase
@@ -180,7 +183,7 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += TW * 5 * seg_cap * 4; o = align_up(o, 128); }
   for (int b = 0; b < 2; ++b) { L.segtab[b] = o; o += TW * nvis * 16; }
   L.gtab = o; o += TW * n_group * nvis * 16;
-  for (int b = 0; b < 2; ++b) { L.gcull[b] = o; o += TW * n_group * 32; }
+  for (int b = 0; b < 2; ++b) { L.gcull[b] = o; o += TW * n_group * (int)sizeof(GroupCull); }
   L.gcnt = o; o += align_up(TW * n_group * 8, 16);
   L.gidx = o; o += align_up(TW * n_group * nvis * 2, 16);
   for (int b = 0; b < 2; ++b) { L.ws[b] = o; o += TW * R * BRS_WS_STRIDE * 8; }
@@ -546,6 +549,26 @@ __device__ BRS_INL_CAMCOL void camera_column(const KParams& p, const CameraDev& 
 // and pictures -- TABLE, SENSE, PAINT -- of tile n.  The teams meet once per tile
 // (__syncthreads); inside a team phases are separated by named barriers.
 // ------------------------------------------------------------------------------
+// One entry of the shared-origin table: m = (ey, -ex)/na, q = d/na with d = O - P,
+// na = ex*dy - ey*dx; false when no ray of the group can hit the segment (degenerate,
+// its line beyond the group's range, or entirely outside the cone of its rays).
+__device__ __forceinline__ bool table_entry(const float4 s, const GroupCull& gc, float4& t) {
+  const float dx = gc.ox - s.x, dy = gc.oy - s.y;
+  const float na = fmaf(s.z, dy, -(s.w * dx));
+  const float ee = fmaf(s.z, s.z, s.w * s.w);
+  bool keep = fabsf(na) > 1e-30f && na * na <= gc.range2 * ee;  // distance to the wall's line
+  if (gc.has_cone) {
+    const float ax = -dx, ay = -dy, bx = s.z - dx, by = s.w - dy;  // end points seen from the origin
+    const bool out_lo = (gc.lo_x * ay - gc.lo_y * ax < 0.f) && (gc.lo_x * by - gc.lo_y * bx < 0.f);
+    const bool out_hi = (ax * gc.hi_y - ay * gc.hi_x < 0.f) && (bx * gc.hi_y - by * gc.hi_x < 0.f);
+    const bool behind = (gc.ax_x * ax + gc.ax_y * ay < 0.f) && (gc.ax_x * bx + gc.ax_y * by < 0.f);
+    keep = keep && !(out_lo || out_hi || behind);
+  }
+  const float inv = rcp_approx(na);
+  t = make_float4(s.w * inv, -s.z * inv, dx * inv, dy * inv);
+  return keep;
+}
+
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f.one ? n : __umulhi(n, f.mul); }
 __device__ __forceinline__ void team_sync(int id, int nthreads) {
   if (nthreads == 32)
@@ -800,6 +823,9 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
           gc.ax_x = cf * gd.ax_c - sf * gd.ax_s; gc.ax_y = sf * gd.ax_c + cf * gd.ax_s;
           gc.range2 = gd.range * gd.range;
           gc.has_cone = gd.has_cone;
+          gc.ox = (float)x1;
+          gc.oy = (float)y1;
+          gc._pad[0] = gc._pad[1] = 0.f;
           gcull[wl * NG + g] = gc;
         }
       }
@@ -832,18 +858,21 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
   const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
   const bool do_rays = do_sense || do_cam;
 
-  // ---- prologue: barriers, camera tables
+  // ---- prologue: the helper initialises the TMA barriers and goes straight to the first
+  // tile; the workers meanwhile load the camera tables (iteration -1 gives them nothing
+  // else to do), both meet at that iteration's barrier
   if (tid == NW) {
     mbar_init(smem_u32(&mbar[0]), 1);
     mbar_init(smem_u32(&mbar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < p.n_camera * p.cam_w; i += NT) camcs[i] = p.cam_cs[i];
-  for (int i = tid; i < p.cam_h; i += NT) {
-    rowsky[i] = p.row_sky[i];
-    rowgnd[i] = p.row_gnd[i];
+  if (!is_helper) {
+    for (int i = tid; i < p.n_camera * p.cam_w; i += NW) camcs[i] = p.cam_cs[i];
+    for (int i = tid; i < p.cam_h; i += NW) {
+      rowsky[i] = p.row_sky[i];
+      rowgnd[i] = p.row_gnd[i];
+    }
   }
-  __syncthreads();
 
   // paint mapping: worker thread -> (picture slot, row slot, column quad)
   const int pQ = max(p.cam_w >> 2, 1), pQc = min(pQ, NW);  // pictures wider than 4 x NW: several quads per thread
@@ -860,7 +889,8 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       if (tid == NW) {
         // next tile index + TMA of its wall store into the other buffer (free since the
         // barrier that ended the previous iteration)
-        const int tn = (int)atomicAdd(&p.sched[0], 1u);
+        // (the first tile of a CTA is its block index; the counter hands out the rest)
+        const int tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
         sched[1 + (buf ^ 1)] = tn;
         if (tn < p.n_tiles) {
           const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
@@ -898,32 +928,46 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       // conservative, with margins far above FP32 error).  Survivors are then compacted
       // in index order by one warp per (world, group), so the search loops over fewer
       // entries and ties still resolve as in the reference.
-      if (NG > 0) {
+      if (NG > 0 && p.fused_table) {
+        // enough (world, group) pairs to occupy the warps: build and compact in one pass
+        const int warp = tid >> 5, nwarp = NW >> 5;
+        for (int pg = warp; pg < nw * NG; pg += nwarp) {
+          const int wl = (int)fdiv(pg, p.dNG), g = pg - wl * NG;
+          const int S = meta[wl].x, nv = S + 4 * R, own = S + 4 * p.groups[g].robot;
+          const GroupCull gc = gcull[pg];
+          const float4* st = segtab + (size_t)wl * nvis;
+          float4* tab = gtab + (size_t)pg * nvis;
+          uint16_t* ix = gidx + (size_t)pg * nvis;
+          int base = 0, cw = 0;
+          for (int j0 = 0; j0 < nv; j0 += 32) {
+            const int j = j0 + lane;
+            float4 t;
+            bool keep = false;
+            if (j < nv && (unsigned)(j - own) >= 4u) keep = table_entry(st[j], gc, t);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (keep) {
+              tab[pos] = t;
+              ix[pos] = (uint16_t)j;
+            }
+            const int nwall = S - j0;  // lanes below this index hold walls
+            cw += __popc(nwall >= 32 ? bal : (nwall <= 0 ? 0u : (bal & ((1u << nwall) - 1u))));
+            base += __popc(bal);
+          }
+          if (lane == 0) gcnt[pg] = make_int2(cw, base);
+        }
+        team_sync(1, NW);
+      } else if (NG > 0) {
+        // few pairs with many segments: all threads build, then one warp per pair compacts
         const int per_world = NG * nvis;
         for (int i = tid; i < nw * per_world; i += NW) {
           const int wl = (int)fdiv(i, p.dTab), k = i - wl * per_world;
           const int g = (int)fdiv(k, p.dNvis), j = k - g * nvis;
-          const int S = meta[wl].x, nv = S + 4 * R;
+          const int S = meta[wl].x, nv = S + 4 * R, own = S + 4 * p.groups[g].robot;
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < nv && !(j >= S && ((j - S) >> 2) == p.groups[g].robot)) {
-            const float4 s = segtab[(size_t)wl * nvis + j];
-            const double2 O = org[wl * NG + g];
-            const GroupCull gc = gcull[wl * NG + g];
-            const float dx = (float)(O.x - (double)s.x), dy = (float)(O.y - (double)s.y);
-            const float na = fmaf(s.z, dy, -(s.w * dx));
-            const float ee = fmaf(s.z, s.z, s.w * s.w);
-            bool keep = fabsf(na) > 1e-30f && na * na <= gc.range2 * ee;  // distance to the wall's line
-            if (gc.has_cone) {
-              const float ax = -dx, ay = -dy, bx = s.z - dx, by = s.w - dy;  // end points seen from the origin
-              const bool out_lo = (gc.lo_x * ay - gc.lo_y * ax < 0.f) && (gc.lo_x * by - gc.lo_y * bx < 0.f);
-              const bool out_hi = (ax * gc.hi_y - ay * gc.hi_x < 0.f) && (bx * gc.hi_y - by * gc.hi_x < 0.f);
-              const bool behind = (gc.ax_x * ax + gc.ax_y * ay < 0.f) && (gc.ax_x * bx + gc.ax_y * by < 0.f);
-              keep = keep && !(out_lo || out_hi || behind);
-            }
-            if (keep) {
-              const float inv = rcp_approx(na);
-              t = make_float4(s.w * inv, -s.z * inv, dx * inv, dy * inv);
-            }
+          if (j < nv && (unsigned)(j - own) >= 4u) {
+            float4 u;
+            if (table_entry(segtab[(size_t)wl * nvis + j], gcull[wl * NG + g], u)) t = u;
           }
           gtab[(size_t)wl * per_world + k] = t;
         }
