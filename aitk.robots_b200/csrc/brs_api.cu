@@ -55,7 +55,7 @@ struct brs_engine {
   unsigned int* d_sched = nullptr;
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
-  int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
+  int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
   int gtasks = 0, dtasks = 0;
   bool big = false;
   const void* kfn = nullptr;
@@ -402,7 +402,14 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   // worlds per tile: as many as the budget allows (amortises barriers, fills the lanes of
   // the per-robot phases) while keeping >= ~6 tiles per resident CTA for the dynamic scheduler; among
   // those prefer the count whose ray tasks fill whole passes of the workers
-  int tw_max = std::min(64, std::max(1, cfg->n_worlds / (e->sm_count * (e->big ? BRS_BIG_CTAS : BRS_SMALL_CTAS) * 6)));
+  // tiles per resident CTA slot: ~6 for worlds with real work (tail balance), ~2 for tiny
+  // worlds whose tile time is a latency chain rather than work (estimate in lane-instructions)
+  const int slots = e->sm_count * (e->big ? BRS_BIG_CTAS : BRS_SMALL_CTAS);
+  const double rays = (double)ncols + e->rays_range + (double)cfg->n_light * cfg->n_bulbs;
+  const double nseg = cfg->seg_cap + 4.0 * (R - 1);
+  const double work = (4.0 * R + rays) * nseg * 12.0 + (double)ncols * e->cam_h * 1.5 + rays * 200.0 + R * 1500.0;
+  const int per_slot = work < 20000.0 ? 2 : 6;
+  int tw_max = std::min(64, std::max(1, cfg->n_worlds / (slots * per_slot)));
   while (tw_max > 1 && smem_for(tw_max) > budget) --tw_max;
   int tw = tw_max;
   {
@@ -426,7 +433,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->T = e->NW + 32 * e->NH;
   e->GS = std::min(e->NW, std::max(8, pow2ceil(cfg->seg_cap)));
   e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * tw), 1))) : 1;
-  e->SLD = dtasks ? std::min(32, pow2floor(std::max(e->NW / (dtasks * tw), 1))) : 1;
+  e->SLD = e->n_dr ? std::min(32, pow2floor(std::max(e->NW / (e->n_dr * tw), 1))) : 1;
+  e->SLL = cfg->n_light ? std::min(32, pow2floor(std::max(e->NW / (cfg->n_light * tw), 1))) : 1;
   {
     const int Q = std::max(e->cam_w / 4, 1);
     const int slots = std::max(e->NW / std::min(Q, e->NW), 1);
@@ -529,7 +537,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.n_range = c.n_range; p.n_camera = c.n_camera; p.n_light = c.n_light; p.n_smell = c.n_smell;
   p.cam_w = e->cam_w; p.cam_h = e->cam_h;
   p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
-  p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.paint_rs = e->paint_rs;
+  p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.SLL = e->SLL; p.paint_rs = e->paint_rs;
   p.flat_rows = e->flat_rows;
   p.fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
   p.NW = e->NW; p.NH = e->NH;
@@ -540,7 +548,9 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
     const bool cam = (flags & BRS_STEP_CAMERA) && c.n_camera > 0, sense = flags & BRS_STEP_SENSE;
     const int cblocks = cam ? c.n_camera * (e->cam_w / e->NR) : 0;
     p.dGT = make_fastdiv(std::max(cblocks + (sense ? e->n_gr : 0), 1));
-    p.dDT = make_fastdiv(std::max(e->n_dr + c.n_light + c.n_smell, 1));
+    p.dDT = make_fastdiv(std::max(e->n_dr, 1));
+    p.dLT = make_fastdiv(std::max(c.n_light, 1));
+    p.dST = make_fastdiv(std::max(c.n_smell, 1));
     p.dCpb = make_fastdiv(std::max(e->cam_w / std::max(e->NR, 1), 1));
   }
   p.cull_margin = 0.05f;

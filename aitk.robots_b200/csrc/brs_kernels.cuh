@@ -109,14 +109,14 @@ struct KParams {
   int TW;            // worlds per tile
   int n_tiles;
   int GS;            // threads per (world, robot) in the wall-collision phase (power of two)
-  int SLG, SLD;      // lanes per ray task: group path, direct path (powers of two <= 32)
+  int SLG, SLD, SLL; // lanes per ray task: group path, direct range path, light path (powers of two <= 32)
   int n_gr, n_dr;    // range sensors on the group path / on the direct path
   int paint_rs;      // row slots of the paint phase
   int fused_table;   // TABLE phase: one warp per (world, group) builds and compacts in one pass
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
   int NH;            // helper warps: prepare the next tile during the SENSE phase
-  FastDiv dR, dSC, dTab, dNvis, dPair, dGT, dDT, dCpb, dNG;
+  FastDiv dR, dSC, dTab, dNvis, dPair, dGT, dDT, dLT, dST, dCpb, dNG;
   unsigned flags;
   double dt, smell_cell, light_mult;
   float cull_margin;
@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
             const int pg = wl * NG + sd.group;
             const float4* tab = gtab + (size_t)pg * nvis;
             const int ct = gcnt[pg].y;
-            double reading = 1.0;
+            double best = sd.max;  // the reading stays at max unless a ray hits nearer
             for (int k = 0; k < sd.n_rays; ++k) {
               const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
               const double dyu = da(dm(sa, sd.cr[k]), dm(ca, sd.sr[k]));
@@ -1081,101 +1081,109 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
               else
                 search_group<1, false>(tab, 0, ct, g, SL, rx, ry, key, idx);
               if (SL > 1) group_max(key[0], idx[0], SL, gmask);
-              if (g == 0 && idx[0] >= 0) {
-                const double d = refine64(raw, SC, S, ws, gidx[(size_t)pg * nvis + idx[0]], O.x, O.y, x2, y2);
-                if (d < dm(reading, sd.max)) reading = d / sd.max;
-              }
+              if (g == 0 && idx[0] >= 0) best = fmin(best, refine64(raw, SC, S, ws, gidx[(size_t)pg * nvis + idx[0]], O.x, O.y, x2, y2));
             }
-            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)dm(reading, sd.max);
+            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
           }
         }
       }
-      // 5b. direct path: range sensors on their own mount, light and smell sensors
-      if (do_sense) {
+      // 5b. direct path, one homogeneous loop per device kind (mixing kinds in a warp would
+      //     serialise their code paths): range sensors on their own mount, ...
+      if (do_sense && p.n_dr > 0) {
         const int SL = p.SLD, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
         const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
-        const int ntask = p.n_dr + p.n_light + p.n_smell;
+        const int ntask = p.n_dr;
         for (int i = slot; i < nw * ntask; i += nslot) {
           const int wl = (int)fdiv(i, p.dDT), task = i - wl * ntask, w = w0 + wl;
           const int S = meta[wl].x, nseg = S + 4 * R;
           const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
           const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
           const float4* st = segtab + (size_t)wl * nvis;
-          if (task < p.n_dr) {
-            // RangeSensor.update
-            const int si = p.dr_idx[task];
-            const RangeDev& sd = p.ranges[si];
-            const int r = sd.robot;
-            double x1, y1, ca, sa;
-            mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
-            const float ox = (float)x1, oy = (float)y1;
-            const int own_lo = S + 4 * r, own_hi = own_lo + 4;
-            double reading = 1.0;
-            for (int k = 0; k < sd.n_rays; ++k) {
-              const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
-              const double dyu = da(dm(sa, sd.cr[k]), dm(ca, sd.sr[k]));
-              const double x2 = da(dm(dxu, sd.max), x1), y2 = da(dm(dyu, sd.max), y1);
-              const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
-              uint32_t key = BRS_KEY_NOHIT;
-              int idx = -1;
-              if (SL == 1) {
-                search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
-                search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
-              } else {
-                search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-                search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-                group_min(key, idx, SL, gmask);
-              }
-              if (g == 0 && idx >= 0) {
-                const double d = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2);
-                if (d < dm(reading, sd.max)) reading = d / sd.max;
-              }
+          // RangeSensor.update
+          const int si = p.dr_idx[task];
+          const RangeDev& sd = p.ranges[si];
+          const int r = sd.robot;
+          double x1, y1, ca, sa;
+          mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
+          const float ox = (float)x1, oy = (float)y1;
+          const int own_lo = S + 4 * r, own_hi = own_lo + 4;
+          double best = sd.max;  // the reading stays at max unless a ray hits nearer
+          for (int k = 0; k < sd.n_rays; ++k) {
+            const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
+            const double dyu = da(dm(sa, sd.cr[k]), dm(ca, sd.sr[k]));
+            const double x2 = da(dm(dxu, sd.max), x1), y2 = da(dm(dyu, sd.max), y1);
+            const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
+            uint32_t key = BRS_KEY_NOHIT;
+            int idx = -1;
+            if (SL == 1) {
+              search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
+              search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
+            } else {
+              search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+              search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+              group_min(key, idx, SL, gmask);
             }
-            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)dm(reading, sd.max);
-          } else if (task < p.n_dr + p.n_light) {
-            // LightSensor.update: line of sight to every bulb
-            const int li = task - p.n_dr;
-            const PointDev& sd = p.lights[li];
-            const int r = sd.robot;
-            double x1, y1, ca, sa;
-            mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
-            const float ox = (float)x1, oy = (float)y1;
-            const int own_lo = S + 4 * r, own_hi = own_lo + 4;
-            double value = 0.0;
-            for (int b = 0; b < p.n_bulbs; ++b) {
-              const float* bl = p.bulbs + ((size_t)w * p.n_bulbs + b) * 4;
-              const double bx = (double)bl[0], by = (double)bl[1], br = (double)bl[3];
-              const double ex = ds(bx, x1), ey = ds(by, y1);
-              const double dist = sqrt(da(dm(ex, ex), dm(ey, ey)));
-              const float rx = (float)ex, ry = (float)ey;
-              uint32_t key = BRS_KEY_NOHIT;
-              int idx = -1;
-              if (SL == 1) {
-                search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
-                search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
-              } else {
-                search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-                search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-                group_min(key, idx, SL, gmask);
-              }
-              if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
-            }
-            if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
-          } else {
-            // SmellSensor.update: grid lookup at the mount point
-            const int si = task - p.n_dr - p.n_light;
-            const PointDev& sd = p.smells[si];
-            const int r = sd.robot;
-            double x1, y1, ca, sa;
-            mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
-            float v = 0.f;
-            if (p.grid_w > 0) {
-              const int gx = (int)(x1 / p.smell_cell), gy = (int)(y1 / p.smell_cell);
-              if (gx >= 0 && gx < p.grid_w && gy >= 0 && gy < p.grid_h)
-                v = p.grid[((size_t)w * p.grid_h + gy) * p.grid_w + gx];
-            }
-            if (g == 0) p.smell_out[(size_t)w * p.n_smell + si] = v;
+            if (g == 0 && idx >= 0) best = fmin(best, refine64(raw, SC, S, ws, idx, x1, y1, x2, y2));
           }
+          // (upstream stores reading = d / max and returns reading * max: the float32
+          //  observation cannot see that round trip)
+          if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
+        }
+      }
+      // ... light sensors: line of sight to every bulb ...
+      if (do_sense && p.n_light > 0) {
+        const int SL = p.SLL, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
+        const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
+        const int ntask = p.n_light;
+        for (int i = slot; i < nw * ntask; i += nslot) {
+          const int wl = (int)fdiv(i, p.dLT), li = i - wl * ntask, w = w0 + wl;
+          const int S = meta[wl].x, nseg = S + 4 * R;
+          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+          const float4* st = segtab + (size_t)wl * nvis;
+          const PointDev& sd = p.lights[li];
+          const int r = sd.robot;
+          double x1, y1, ca, sa;
+          mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
+          const float ox = (float)x1, oy = (float)y1;
+          const int own_lo = S + 4 * r, own_hi = own_lo + 4;
+          double value = 0.0;
+          for (int b = 0; b < p.n_bulbs; ++b) {
+            const float* bl = p.bulbs + ((size_t)w * p.n_bulbs + b) * 4;
+            const double bx = (double)bl[0], by = (double)bl[1], br = (double)bl[3];
+            const double ex = ds(bx, x1), ey = ds(by, y1);
+            const double dist = sqrt(da(dm(ex, ex), dm(ey, ey)));
+            const float rx = (float)ex, ry = (float)ey;
+            uint32_t key = BRS_KEY_NOHIT;
+            int idx = -1;
+            if (SL == 1) {
+              search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
+              search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
+            } else {
+              search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+              search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+              group_min(key, idx, SL, gmask);
+            }
+            if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
+          }
+          if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
+        }
+      }
+      // ... smell sensors: grid lookup at the mount point
+      if (do_sense && p.n_smell > 0) {
+        const int ntask = p.n_smell;
+        for (int i = tid; i < nw * ntask; i += NW) {
+          const int wl = (int)fdiv(i, p.dST), si = i - wl * ntask, w = w0 + wl;
+          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+          const PointDev& sd = p.smells[si];
+          double x1, y1, ca, sa;
+          mount_point(ws + sd.robot * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
+          float v = 0.f;
+          if (p.grid_w > 0) {
+            const int gx = (int)(x1 / p.smell_cell), gy = (int)(y1 / p.smell_cell);
+            if (gx >= 0 && gx < p.grid_w && gy >= 0 && gy < p.grid_h)
+              v = p.grid[((size_t)w * p.grid_h + gy) * p.grid_w + gx];
+          }
+          p.smell_out[(size_t)w * p.n_smell + si] = v;
         }
       }
 
