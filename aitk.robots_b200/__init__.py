@@ -21,6 +21,7 @@ from .scenes import (  # noqa: F401
 from . import scenes  # noqa: F401
 from .world import Bulb, Camera, LightSensor, RangeSensor, Robot, SmellSensor, World  # noqa: F401
 from .sharding import ShardedWorlds  # noqa: F401
+from .vec_env import VecEnv  # noqa: F401
 
 STEP_MOVE, STEP_SENSE, STEP_CAMERA, STEP_ALL = _cabi.STEP_MOVE, _cabi.STEP_SENSE, _cabi.STEP_CAMERA, _cabi.STEP_ALL
 __version__ = "0.1.0"

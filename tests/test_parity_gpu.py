@@ -167,7 +167,8 @@ def _outputs(scene, steps, env):
 
 
 @pytest.mark.parametrize("maker", [
-    lambda: rb.scenes.config4(n_worlds=256),
+    lambda: rb.scenes.config2(n_worlds=256),
+    lambda: rb.scenes.config4(n_worlds=2048),
     lambda: rb.scenes.config4(n_worlds=128, variant="random"),
     lambda: rb.scenes.config5(n_worlds=64, n_segments=300, n_rays=16),
     lambda: rb.scenes.demo_scene(64),
@@ -230,3 +231,69 @@ def test_many_steps_stalled_robots_config4():
     scene.target_vel[:, :, 0] = 2.0  # full speed ahead
     stats = parity.compare(scene, n_steps=60, camera=False)
     assert stats["max_pose_err"] < 1e-9
+
+
+def _crowd_scene(n_worlds, n_robots, seed=11):
+    """Many robots in a small room: robot-robot collisions are frequent (exercises the
+    list-order replay on the pair masks up to BRS_MAX_ROBOTS)."""
+    import math
+
+    g = rb.scenes
+    rng = g._rng(seed, 0)
+    w, h, B = 120.0, 100.0, n_worlds
+    bx = np.array(g._boundary(w, h), dtype=np.float32)
+    segs = [np.tile(bx[None, :, k], (B, 1)) for k in range(4)]
+    colors = np.tile(np.array([[(128, 0, 128, 255)] * 4], dtype=np.uint8), (B, 1, 1))
+    robots = []
+    for k in range(n_robots):
+        devs = [g.RangeSpec(position=(8.0, 0.0), a=0.0, max=60.0, width=20.0 if k % 2 else 0.0)]
+        if k == 0:
+            devs.append(g.CameraSpec(width=32, height=16, a=90.0))
+        robots.append(g.RobotSpec(rgba=tuple(int(c) for c in g.PALETTE[k % 8]), height=0.3 + 0.05 * k, devices=devs))
+    scene = g._assemble("crowd", w, h, segs, colors, robots, rng, B)
+    scene.target_vel[:, :, 0] = rng.uniform(1.0, 2.0, (B, n_robots))
+    return scene
+
+
+@pytest.mark.parametrize("n_robots", [2, 5, 8])
+def test_crowded_rooms_up_to_max_robots(n_robots):
+    scene = _crowd_scene(12, n_robots)
+    stats = parity.compare(scene, n_steps=40, camera=True)
+    assert stats["max_pose_err"] < 1e-9
+    # the rooms are crowded enough that robots do collide with each other
+    out = parity.run_engine(scene, 40)
+    assert out["stalled"].any()
+
+
+def test_vec_env_matches_oracle_and_auto_resets():
+    """The gym-style wrapper: device-resident actions in, zero-copy observations out; the
+    trajectory equals the oracle driven with the same Robot.move() calls."""
+    import torch
+
+    from oracle import scene_adapter as sa
+
+    scene = rb.scenes.config2(n_worlds=16, cam_w=32, cam_h=16)
+    env = rb.VecEnv(scene, max_steps=4)
+    obs = env.reset()
+    assert obs["camera"].is_cuda and obs["camera"].shape == (16, 1, 16, 32, 4)
+    gen = torch.Generator().manual_seed(0)
+    acts = [torch.rand((16, 1, 2), generator=gen) * 2 - 1 for _ in range(3)]
+    worlds = {i: sa.build_world(scene, i) for i in (0, 9)}
+    for a in acts:
+        obs, reward, done, info = env.step(a.cuda())
+        assert not bool(done.any()) and reward.shape == (16,)
+        for i, (w, devs) in worlds.items():
+            w._robots[0].move(float(a[i, 0, 0]), float(a[i, 0, 1]))
+            w.step()
+            ref = sa.observe(w, devs, camera=False)
+            assert abs(float(env.pose[i, 0, 0]) - ref["pose"][0][0]) < 1e-9
+            assert int(env.stalled[i, 0]) == ref["stalled"][0]
+            np.testing.assert_allclose(obs["range"][i].cpu().numpy(), ref["range"], rtol=1e-4)
+    # 4th step ends every episode: worlds restart from their initial poses with fresh observations
+    obs, reward, done, info = env.step(acts[0].cuda())
+    assert bool(done.all()) and int(env.steps.max()) == 0
+    assert torch.allclose(env.pose.cpu(), torch.as_tensor(scene.pose))
+    first = rb.VecEnv(scene, max_steps=4)
+    assert torch.equal(first.reset()["range"].cpu(), obs["range"].cpu())
+    first.close()
+    env.close()
