@@ -584,7 +584,7 @@ __device__ __forceinline__ void team_sync(int id, int nthreads) {
 __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
                                              const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
                                              double* __restrict__ wsb, int4* __restrict__ cflag,
-                                             int2* __restrict__ meta) {
+                                             int2* __restrict__ meta, uint32_t bar, uint32_t parity) {
   const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
   for (int i = ht; i < nw * R; i += nth) {
     const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
@@ -639,6 +639,8 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
     meta[wl].x = min(max(p.seg_count[w], 0), SC);
     meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
   }
+  // the tile's wall store was requested before the robot state: by now it has usually landed
+  mbar_wait(bar, parity);
   for (int i = ht; i < nw * SC; i += nth) {
     const int wl = (int)fdiv(i, p.dSC), j = i - wl * SC;
     const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
@@ -655,9 +657,10 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
                                                 bool do_rays, const uint32_t* __restrict__ rawb,
                                                 float4* __restrict__ segtab, double* __restrict__ wsb,
                                                 int4* __restrict__ cflag, int2* __restrict__ meta,
-                                                double2* __restrict__ org, GroupCull* __restrict__ gcull) {
+                                                double2* __restrict__ org, GroupCull* __restrict__ gcull, uint32_t bar,
+                                                uint32_t parity) {
   const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
-  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta);
+  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, bar, parity);
   team_sync(2, nth);
   if (do_move) {
     // ---------------- COLLIDE ------------------------------------------------------
@@ -903,11 +906,11 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       const int tn = sched[1 + (buf ^ 1)];
       if (tn < p.n_tiles) {
         const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-        mbar_wait(smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
         robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, (const uint32_t*)(smem + L.raw[buf ^ 1]),
                         (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
                         (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
-                        (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]));
+                        (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
+                        smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
       }
     } else if (do_rays && it >= 0) {
       // ================= workers: sensors and pictures of THIS tile ====================

@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (default: the BASELINE.json size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-large-batch", action="store_true",
+                    help="skip the supplementary run at 4x the worlds (shows the launch prologue/tail share)")
     ap.add_argument("--gather", action="store_true", help="also time the optional NCCL observation all-gather")
     args = ap.parse_args()
     if not args.worlds:
@@ -407,13 +409,36 @@ def main():
         }
         if gather:
             line["gather"] = gather
+        if world_size == 1 and not args.no_large_batch and 4 * alg_bytes < 16e9:
+            # supplementary: the same workload at 4x the worlds.  A launch of the named size lasts
+            # ~0.1 ms, of which the pipeline fill (first tile of every CTA) and the tail are a fixed
+            # ~20 us; the larger batch shows the kernel's steady-state rate.  Not the headline.
+            eng.close()
+            eng = None
+            big = rb.BatchEngine(make_scene(rb, args.config, 4 * B, 50_000_000), device=local_rank)
+            for _ in range(3):
+                big.step(flags=flags, stream=sh)
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(stream)
+            for _ in range(args.steps):
+                big.step(flags=flags, stream=sh)
+            b1.record(stream)
+            torch.cuda.synchronize()
+            bms = b0.elapsed_time(b1) / args.steps
+            line["large_batch"] = {"worlds_per_gpu": 4 * B, "ms_per_step": bms, "value": 4 * B / (bms * 1e-3),
+                                   "hbm_frac": 4 * alg_bytes / (bms * 1e-3) / 1e9 / hbm_peak,
+                                   "fp32_frac": 4 * tests_per_step * FLOPS_PER_TEST / (bms * 1e-3) / 1e12
+                                   / (ffma_tflops or NOMINAL_FP32_TFLOPS)}
+            big.close()
         if not args.no_cpu_baseline and world_size == 1:
             r = cpu_throughput(args.config, args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["world_steps_per_sec"], "unit": "world-steps/s", "cores": r["cores"],
                                     "kind": "port", "sample": r["sample"],
                                     "ray_segment_tests_per_sec": r["tests_per_sec"]}
         print(json.dumps(line))
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
