@@ -390,14 +390,33 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->gtasks = gtasks;
   e->dtasks = dtasks;
   const int tasks = std::max(gtasks + dtasks, 1);
-  auto smem_for = [&](int tw) { return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h).total; };
-  // small shape (128 workers, 4 CTAs/SM) unless one world's footprint leaves room for <= 2 CTAs
+  auto smem_shape = [&](int tw, bool big) {
+    return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h, !big).total;
+  };
+  // small shape (128 workers, 4 CTAs/SM, TMA-staged walls) unless one world's footprint leaves
+  // room for <= 2 such CTAs; the big shape (256 workers) reads walls from L2 instead of staging
   const int smem_sm = (int)prop.sharedMemPerMultiprocessor - 4096;
-  e->big = smem_for(1) > smem_sm / 3;
+  e->big = smem_shape(1, false) > smem_sm / 3;
   e->big = env_int("BRS_BIG", e->big ? 1 : 0) != 0;
-  e->NW = env_int("BRS_NW", e->big ? 256 : 128);
-  if (e->NW != 64 && e->NW != 128 && e->NW != 192 && e->NW != 256) e->NW = e->big ? 256 : 128;
-  if (!e->big && e->NW > 128) e->NW = 128;
+  auto smem_for = [&](int tw) { return smem_shape(tw, e->big); };
+  // split of the CTA between the helper team (Robot.step: wall table, collision cull over all
+  // walls) and the workers (rays): in proportion to their work per world, in warps.  Worlds
+  // with many walls and few rays get more helpers, camera worlds the minimum of one warp.
+  const int T_total = e->big ? BRS_BIG_THREADS : BRS_SMALL_THREADS;
+  {
+    const double S = cfg->seg_cap + 4.0 * (R - 1);
+    const double grays = (double)ncols, rrays = (double)e->rays_range, lrays = (double)cfg->n_light * cfg->n_bulbs;
+    const double grp_rays = grays + (e->n_gr ? rrays : 0.0), dir_rays = (e->n_gr ? 0.0 : rrays) + lrays;
+    const double helper_w = R * (cfg->seg_cap * 40.0 + 1500.0);
+    const double worker_w = grp_rays * S * 6.0 + dir_rays * S * 17.0 + (grays + rrays + lrays) * 250.0 +
+                            e->n_group * S * 45.0 + (double)ncols * e->cam_h * 1.5;
+    int nh = (int)std::lround(T_total / 32.0 * helper_w / (helper_w + worker_w));
+    nh = std::max(1, std::min(nh, T_total / 32 - 1));
+    nh = env_int("BRS_NH", nh);
+    nh = std::max(1, std::min(nh, T_total / 32 - 1));
+    e->NH = nh;
+    e->NW = T_total - 32 * nh;
+  }
   const int budget = env_int("BRS_SMEM_BUDGET", e->big ? smem_sm / BRS_BIG_CTAS : smem_sm / BRS_SMALL_CTAS);
   // worlds per tile: as many as the budget allows (amortises barriers, fills the lanes of
   // the per-robot phases) while keeping >= ~6 tiles per resident CTA for the dynamic scheduler; among
@@ -429,9 +448,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     return fail(BRS_ERR_UNSUPPORTED, "brs_create: world too large for one CTA's shared memory (seg_cap / camera width / groups)");
   }
   e->n_tiles = (cfg->n_worlds + tw - 1) / tw;
-  e->NH = 1;  // one helper warp prepares the next tile (launch bound: NW + 32 <= 288 threads)
   e->T = e->NW + 32 * e->NH;
-  e->GS = std::min(e->NW, std::max(8, pow2ceil(cfg->seg_cap)));
+  e->GS = std::min(32 * e->NH, std::max(8, pow2ceil(cfg->seg_cap)));  // helper threads per (world, robot)
   e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * tw), 1))) : 1;
   e->SLD = e->n_dr ? std::min(32, pow2floor(std::max(e->NW / (e->n_dr * tw), 1))) : 1;
   e->SLL = cfg->n_light ? std::min(32, pow2floor(std::max(e->NW / (cfg->n_light * tw), 1))) : 1;
@@ -543,7 +561,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.NW = e->NW; p.NH = e->NH;
   {
     const int R = c.n_robots, nvis = c.seg_cap + 4 * R;
-    p.dR = make_fastdiv(R); p.dSC = make_fastdiv(c.seg_cap); p.dTab = make_fastdiv(std::max(e->n_group * nvis, 1));
+    p.dR = make_fastdiv(R); p.dSC = make_fastdiv(c.seg_cap); p.dSQ = make_fastdiv(c.seg_cap / 4); p.dTab = make_fastdiv(std::max(e->n_group * nvis, 1));
     p.dNvis = make_fastdiv(nvis); p.dPair = make_fastdiv(R * R * 2); p.dNG = make_fastdiv(std::max(e->n_group, 1));
     const bool cam = (flags & BRS_STEP_CAMERA) && c.n_camera > 0, sense = flags & BRS_STEP_SENSE;
     const int cblocks = cam ? c.n_camera * (e->cam_w / e->NR) : 0;

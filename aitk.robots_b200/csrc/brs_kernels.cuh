@@ -116,7 +116,7 @@ struct KParams {
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
   int NH;            // helper warps: prepare the next tile during the SENSE phase
-  FastDiv dR, dSC, dTab, dNvis, dPair, dGT, dDT, dLT, dST, dCpb, dNG;
+  FastDiv dR, dSC, dSQ, dTab, dNvis, dPair, dGT, dDT, dLT, dST, dCpb, dNG;
   unsigned flags;
   double dt, smell_cell, light_mult;
   float cull_margin;
@@ -176,11 +176,12 @@ struct SmemLayout {
 };
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, int n_group, int n_camera, int cam_w,
-                                                  int cam_h) {
+                                                  int cam_h, bool stage_walls) {
   SmemLayout L;
   const int nvis = seg_cap + 4 * R;
   int o = 0;
-  for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += TW * 5 * seg_cap * 4; o = align_up(o, 128); }
+  // the TMA-staged wall store, double buffered (big worlds read walls from L2 / HBM instead)
+  for (int b = 0; b < 2; ++b) { L.raw[b] = o; o += stage_walls ? TW * 5 * seg_cap * 4 : 0; o = align_up(o, 128); }
   for (int b = 0; b < 2; ++b) { L.segtab[b] = o; o += TW * nvis * 16; }
   L.gtab = o; o += TW * n_group * nvis * 16;
   for (int b = 0; b < 2; ++b) { L.gcull[b] = o; o += TW * n_group * (int)sizeof(GroupCull); }
@@ -584,7 +585,7 @@ __device__ __forceinline__ void team_sync(int id, int nthreads) {
 __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
                                              const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
                                              double* __restrict__ wsb, int4* __restrict__ cflag,
-                                             int2* __restrict__ meta, uint32_t bar, uint32_t parity) {
+                                             int2* __restrict__ meta, uint32_t bar, uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
   for (int i = ht; i < nw * R; i += nth) {
     const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
@@ -640,16 +641,25 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
     meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
   }
   // the tile's wall store was requested before the robot state: by now it has usually landed
-  mbar_wait(bar, parity);
-  for (int i = ht; i < nw * SC; i += nth) {
-    const int wl = (int)fdiv(i, p.dSC), j = i - wl * SC;
-    const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
-    const float x1 = __uint_as_float(raw[j]), y1 = __uint_as_float(raw[SC + j]);
-    const float x2 = __uint_as_float(raw[2 * SC + j]), y2 = __uint_as_float(raw[3 * SC + j]);
-    segtab[(size_t)wl * nvis + j] = make_float4(x1, y1, x2 - x1, y2 - y1);
+  if (staged) mbar_wait(bar, parity);
+  // four walls per thread and step: one 16-byte load per SoA row (x1|y1|x2|y2), so that four
+  // independent loads are in flight -- the big shape reads them straight from L2 / HBM
+  const int SQ = SC >> 2;
+#pragma unroll 2
+  for (int i = ht; i < nw * SQ; i += nth) {
+    const int wl = (int)fdiv(i, p.dSQ), q = i - wl * SQ;
+    const uint4* raw = (const uint4*)(rawb + (size_t)wl * 5 * SC);
+    const uint4 X1 = raw[q], Y1 = raw[SQ + q], X2 = raw[2 * SQ + q], Y2 = raw[3 * SQ + q];
+    float4* dst = segtab + (size_t)wl * nvis + 4 * q;
+    const uint32_t x1[4] = {X1.x, X1.y, X1.z, X1.w}, y1[4] = {Y1.x, Y1.y, Y1.z, Y1.w};
+    const uint32_t x2[4] = {X2.x, X2.y, X2.z, X2.w}, y2[4] = {Y2.x, Y2.y, Y2.z, Y2.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float ax = __uint_as_float(x1[k]), ay = __uint_as_float(y1[k]);
+      dst[k] = make_float4(ax, ay, __uint_as_float(x2[k]) - ax, __uint_as_float(y2[k]) - ay);
+    }
   }
 }
-
 
 // Robot.step of one tile by the helper team (thread ht of nth): PREP, then the
 // collision tests, then commit / stall and everything that hangs off the final pose.
@@ -658,9 +668,9 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
                                                 float4* __restrict__ segtab, double* __restrict__ wsb,
                                                 int4* __restrict__ cflag, int2* __restrict__ meta,
                                                 double2* __restrict__ org, GroupCull* __restrict__ gcull, uint32_t bar,
-                                                uint32_t parity) {
+                                                uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
-  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, bar, parity);
+  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, bar, parity, staged);
   team_sync(2, nth);
   if (do_move) {
     // ---------------- COLLIDE ------------------------------------------------------
@@ -845,7 +855,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
   const bool is_helper = tid >= NW;
   const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
   const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
-  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h);
+  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h, !BIG);
   float4* const gtab = (float4*)(smem + L.gtab);
   uint16_t* const gidx = (uint16_t*)(smem + L.gidx);
   int2* const gcnt = (int2*)(smem + L.gcnt);
@@ -895,7 +905,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         // (the first tile of a CTA is its block index; the counter hands out the rest)
         const int tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
         sched[1 + (buf ^ 1)] = tn;
-        if (tn < p.n_tiles) {
+        if (!BIG && tn < p.n_tiles) {
           const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
           mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
           tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
@@ -906,22 +916,25 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       const int tn = sched[1 + (buf ^ 1)];
       if (tn < p.n_tiles) {
         const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, (const uint32_t*)(smem + L.raw[buf ^ 1]),
+        // big worlds (one or two CTAs per SM by their tables alone) do not stage the wall
+        // store: the helper reads it once from L2 / HBM, coalesced, to build the FP32 table
+        const uint32_t* rawn = BIG ? p.seg + (size_t)wn * 5 * SC : (const uint32_t*)(smem + L.raw[buf ^ 1]);
+        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, rawn,
                         (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
                         (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
                         (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
-                        smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u);
+                        smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
       }
     } else if (do_rays && it >= 0) {
       // ================= workers: sensors and pictures of THIS tile ====================
-      const uint32_t* const rawb = (const uint32_t*)(smem + L.raw[buf]);
+      const uint32_t* const rawb = BIG ? p.seg + (size_t)w0 * 5 * SC : (const uint32_t*)(smem + L.raw[buf]);
       const float4* const segtab = (const float4*)(smem + L.segtab[buf]);
       const double* const wsb = (const double*)(smem + L.ws[buf]);
       const int2* const meta = (const int2*)(smem + L.meta[buf]);
       const double2* const org = (const double2*)(smem + L.org[buf]);
       const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
       // every thread observes the phase of this tile's wall store itself before reading it
-      mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+      if (!BIG) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
 
       // ---------------- TABLE ------------------------------------------------------------
       // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,

@@ -208,10 +208,10 @@ def _point_seg_dist(px, py, x1, y1, x2, y2):
     return np.hypot(px - (x1 + t * dx), py - (y1 + t * dy))
 
 
-def _place_robots(rng, seg, seg_count, w, h, R, radius, tries=200):
+def _place_robots(rng, seg, seg_count, w, h, R, radius, tries=200, clear_extra=2.0):
     """Rejection-sample R collision-free robot centres per world (float32-representable)."""
     B = seg.shape[0]
-    clear = radius + 2.0
+    clear = radius + clear_extra
     px = np.zeros((B, R), dtype=np.float32)
     py = np.zeros((B, R), dtype=np.float32)
     valid_seg = np.arange(seg.shape[2])[None, :] < seg_count[:, None]
@@ -239,7 +239,8 @@ def _place_robots(rng, seg, seg_count, w, h, R, radius, tries=200):
     return px, py
 
 
-def _assemble(name, w, h, segs, colors, robots, rng, B, bulbs=None, food=None, smell_cell=0.0, pose=None, vel=None):
+def _assemble(name, w, h, segs, colors, robots, rng, B, bulbs=None, food=None, smell_cell=0.0, pose=None, vel=None,
+              tries=200, clear_extra=2.0):
     x1, y1, x2, y2 = segs
     n = x1.shape[1]
     cap = (n + 3) // 4 * 4
@@ -251,7 +252,7 @@ def _assemble(name, w, h, segs, colors, robots, rng, B, bulbs=None, food=None, s
     R = len(robots)
     if pose is None:
         radius = max(r.radius() for r in robots)
-        px, py = _place_robots(rng, seg, count, w, h, R, radius)
+        px, py = _place_robots(rng, seg, count, w, h, R, radius, tries=tries, clear_extra=clear_extra)
         pa = rng.uniform(0, 2 * math.pi, (B, R))
         pose = np.stack([px.astype(np.float64), py.astype(np.float64), pa], axis=2)
     if vel is None:
@@ -419,7 +420,9 @@ def config5(n_worlds=262144, n_segments=100, n_rays=16, seed=5000, first_world=0
         RangeSpec(position=(0.0, 0.0), a=360.0 * i / n_rays, max=200.0, width=0.0, name="ray%d" % i) for i in range(n_rays)
     ]
     robot = RobotSpec(bbox=(-2.0, 2.0, -2.0, 2.0), devices=devs)
-    return _assemble("config5-S%d-R%d" % (n_segments, n_rays), w, h, segs, colors, [robot], rng, B)
+    # dense cells (2000 walls) leave little free space: small clearance, many tries
+    return _assemble("config5-S%d-R%d" % (n_segments, n_rays), w, h, segs, colors, [robot], rng, B, tries=4000,
+                     clear_extra=0.25)
 
 
 def demo_scene(n_worlds=8, seed=7, first_world=0):
