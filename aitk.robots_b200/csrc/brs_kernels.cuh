@@ -409,16 +409,16 @@ __device__ __forceinline__ void seg64(const uint32_t* raw, int SC, int S, const 
   }
 }
 
-// float64 distance of the hit of ray (x1,y1)->(x2,y2) on segment j, computed
-// like cast_ray: pos = intersect_hit(...), dist = distance(pos, origin)
+// float64 distance of the hit of ray (x1,y1)->(x2,y2) of length `len` on segment j.
+// cast_ray computes pos = intersect_hit(...), dist = distance(pos, origin), i.e.
+// sqrt((ua*rx)^2 + (ua*ry)^2); that equals ua * len to within 2 ulp of float64 (|r| is
+// len times a unit vector), which is 12 orders of magnitude inside the 1e-4 contract, so
+// the square root and its operands are not recomputed per ray.
 __device__ BRS_INL_REFINE double refine64(const uint32_t* raw, int SC, int S, const double* ws, int j, double x1,
-                                           double y1, double x2, double y2) {
+                                           double y1, double x2, double y2, double len) {
   double x3, y3, x4, y4;
   seg64(raw, SC, S, ws, j, x3, y3, x4, y4);
-  const double ua = ua64(x1, y1, x2, y2, x3, y3, x4, y4);
-  const double px = da(x1, dm(ua, ds(x2, x1))), py = da(y1, dm(ua, ds(y2, y1)));
-  const double ex = ds(px, x1), ey = ds(py, y1);
-  return sqrt(da(dm(ex, ex), dm(ey, ey)));
+  return dm(ua64(x1, y1, x2, y2, x3, y3, x4, y4), len);
 }
 
 __device__ __forceinline__ double clamp01(double v) { return fmax(fmin(v, 1.0), 0.0); }
@@ -507,9 +507,10 @@ __device__ BRS_INL_CAMCOL void camera_column(const KParams& p, const CameraDev& 
   ci.rgba = 0; ci.top = -1; ci.bot = -1; ci.n_robot = 0;
   const double H = (double)cd.height;
   if (idx >= 0) {
-    const double dist = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2);
-    const double s = clamp01(ds(1.0, dm(dist / wsize, cd.size_fade)));
-    const double sc = clamp01(ds(1.0, dm(dist / wsize, cd.color_fade)));
+    const double dist = refine64(raw, SC, S, ws, idx, x1, y1, x2, y2, cd.max_range);
+    const double dw = dist / wsize;
+    const double s = clamp01(ds(1.0, dm(dw, cd.size_fade)));
+    const double sc = clamp01(ds(1.0, dm(dw, cd.color_fade)));
     ci.rgba = shade(raw[4 * SC + idx], sc);
     const double high = dm(ds(1.0, s), H);
     ci.top = (int)ceil(high / 2.0);
@@ -1097,7 +1098,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
               else
                 search_group<1, false>(tab, 0, ct, g, SL, rx, ry, key, idx);
               if (SL > 1) group_max(key[0], idx[0], SL, gmask);
-              if (g == 0 && idx[0] >= 0) best = fmin(best, refine64(raw, SC, S, ws, gidx[(size_t)pg * nvis + idx[0]], O.x, O.y, x2, y2));
+              if (g == 0 && idx[0] >= 0) best = fmin(best, refine64(raw, SC, S, ws, gidx[(size_t)pg * nvis + idx[0]], O.x, O.y, x2, y2, sd.max));
             }
             if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
           }
@@ -1139,7 +1140,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
               search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
               group_min(key, idx, SL, gmask);
             }
-            if (g == 0 && idx >= 0) best = fmin(best, refine64(raw, SC, S, ws, idx, x1, y1, x2, y2));
+            if (g == 0 && idx >= 0) best = fmin(best, refine64(raw, SC, S, ws, idx, x1, y1, x2, y2, sd.max));
           }
           // (upstream stores reading = d / max and returns reading * max: the float32
           //  observation cannot see that round trip)
