@@ -172,6 +172,7 @@ def _outputs(scene, steps, env):
     lambda: rb.scenes.config4(n_worlds=128, variant="random"),
     lambda: rb.scenes.config5(n_worlds=64, n_segments=300, n_rays=16),
     lambda: rb.scenes.demo_scene(64),
+    lambda: rb.scenes.config3(n_worlds=96),
 ])
 def test_culling_and_tiling_never_change_results(maker):
     """Cone / range culling, table compaction, tile size and launch shape only remove or
@@ -179,7 +180,7 @@ def test_culling_and_tiling_never_change_results(maker):
     scene = maker()
     base = _outputs(scene, 3, {})
     for env in ({"BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_TW": "1"}, {"BRS_TW": "5", "BRS_BIG": "1"},
-                {"BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
+                {"BRS_NH": "2"}, {"BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
         other = _outputs(scene, 3, env)
         for k in base:
             if k in ("range", "light") and env.get("BRS_GROUP_MIN"):
