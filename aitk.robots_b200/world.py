@@ -237,6 +237,8 @@ class World:
         self._sensed = False
         self._state = {}
         self._obs = {}
+        self._boundary_wall = bool(boundary_wall)
+        self._boundary_color = to_rgba(boundary_wall_color)
         if boundary_wall:
             c = to_rgba(boundary_wall_color)
             w, h = self.width, self.height
@@ -370,6 +372,68 @@ class World:
     def steps(self, n, time_step=None):
         for _ in range(int(n)):
             self.step(time_step)
+
+    # -- scene files ---------------------------------
+    def to_json(self):
+        """The scene as a plain dict (json.dump-able).  Key names follow the upstream
+        ``World.to_json`` layout as recollected ([RECALL]: width / height /
+        boundary_wall / walls[{color, p1, p2}] / bulbs / food / robots[{x, y, a, devices[
+        {class, ...}]}]); it could not be checked against a real aitk scene file here."""
+        nb = 4 if self._boundary_wall else 0
+        walls = [{"color": list(c), "p1": {"x": x1, "y": y1}, "p2": {"x": x2, "y": y2}, "wtype": "line"}
+                 for (x1, y1, x2, y2, c) in self._segments[nb:]]
+        robots = []
+        for r in self._robots:
+            x, y, a = r.get_pose()
+            devs = []
+            for d in r._devices:
+                spec = dict(vars(d.spec))
+                spec["position"] = list(spec["position"])
+                spec["class"] = type(d).__name__
+                devs.append(spec)
+            robots.append({"class": "Robot", "name": r.name, "x": x, "y": y, "a": a / PI_OVER_180,
+                           "color": list(r.color), "height": r.height, "bbox": list(r.bbox),
+                           "max_trans_velocity": r.max_trans_velocity,
+                           "max_rotate_velocity": r.max_rotate_velocity, "devices": devs})
+        return {"width": self.width, "height": self.height, "seed": self.seed,
+                "boundary_wall": self._boundary_wall, "boundary_wall_color": list(self._boundary_color),
+                "ground_color": list(self.ground_color), "smell_cell_size": self.smell_cell_size,
+                "time_step": self.time_step, "walls": walls,
+                "bulbs": [{"color": list(b.color), "x": b.x, "y": b.y, "z": b.z, "brightness": b.brightness,
+                           "name": b.name} for b in self._bulbs],
+                "food": [list(f) for f in self._food], "robots": robots}
+
+    @classmethod
+    def from_json(cls, config, device=0):
+        """Rebuild a World from ``to_json`` output (or a path to a JSON file of it)."""
+        if isinstance(config, str):
+            import json
+
+            with open(config) as f:
+                config = json.load(f)
+        world = cls(config["width"], config["height"], seed=config.get("seed", 0),
+                    boundary_wall=config.get("boundary_wall", True),
+                    boundary_wall_color=config.get("boundary_wall_color", "purple"),
+                    ground_color=config.get("ground_color", "green"),
+                    smell_cell_size=config.get("smell_cell_size"), time_step=config.get("time_step", 0.1),
+                    device=device)
+        for w in config.get("walls", []):
+            world.add_wall(w["color"], w["p1"]["x"], w["p1"]["y"], w["p2"]["x"], w["p2"]["y"],
+                           box=w.get("wtype", "line") == "box")
+        for b in config.get("bulbs", []):
+            world.add_bulb(b["color"], b["x"], b["y"], b.get("z", 0.0), b.get("brightness", 1.0), b.get("name", "bulb"))
+        for f in config.get("food", []):
+            world.add_food(*f)
+        kinds = {"RangeSensor": RangeSensor, "Camera": Camera, "LightSensor": LightSensor, "SmellSensor": SmellSensor}
+        for rc in config.get("robots", []):
+            robot = Robot(rc["x"], rc["y"], rc["a"], color=rc.get("color", "red"), name=rc.get("name", "Robbie"),
+                          height=rc.get("height", 0.25), max_trans_velocity=rc.get("max_trans_velocity", 2.0),
+                          max_rotate_velocity=rc.get("max_rotate_velocity", math.pi / 4), bbox=rc.get("bbox"))
+            for dc in rc.get("devices", []):
+                dc = dict(dc)
+                robot.add_device(kinds[dc.pop("class")](**dc))
+            world.add_robot(robot)
+        return world
 
     def seconds(self, seconds, time_step=None):
         dt = self.time_step if time_step is None else time_step

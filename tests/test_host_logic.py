@@ -92,3 +92,30 @@ def _gloo_worker(rank, ws, port, n_worlds):
 def test_sharded_gather_gloo_world_size_2(n_worlds):
     port = 29500 + (os.getpid() % 2000) + n_worlds
     mp.spawn(_gloo_worker, args=(2, port, n_worlds), nprocs=2, join=True)
+
+
+def test_world_json_round_trip(tmp_path):
+    """World.to_json / from_json: the scene survives a file round trip."""
+    import json
+
+    w = rb.World(200, 150, boundary_wall_color="blue")
+    w.add_wall("red", 50, 20, 50, 120, box=False)
+    w.add_wall("cyan", 120, 40, 140, 60, box=True)
+    w.add_bulb("white", 30, 30, 0, 2.0)
+    w.add_food(160, 100, 25)
+    r = rb.Robot(100, 75, 45, color="yellow", name="A")
+    r.add_device(rb.RangeSensor(position=(8, 0), a=10, max=80, width=5, name="ir"))
+    r.add_device(rb.Camera(width=32, height=16, a=70))
+    r.add_device(rb.LightSensor(position=(6, 0)))
+    r.add_device(rb.SmellSensor(position=(6, 0)))
+    w.add_robot(r)
+    w.add_robot(rb.Robot(40, 100, -90))
+    path = tmp_path / "scene.json"
+    path.write_text(json.dumps(w.to_json()))
+    w2 = rb.World.from_json(str(path))
+    a, b = w.to_scene(2), w2.to_scene(2)
+    assert np.array_equal(a.seg, b.seg) and np.array_equal(a.seg_rgba, b.seg_rgba)
+    assert np.array_equal(a.seg_count, b.seg_count) and int(a.seg_count[0]) == 4 + 1 + 4
+    assert np.allclose(a.pose, b.pose) and np.array_equal(a.bulbs, b.bulbs) and np.array_equal(a.grid, b.grid)
+    assert [type(d).__name__ for d in w2._robots[0]._devices] == ["RangeSensor", "Camera", "LightSensor", "SmellSensor"]
+    assert w2._robots[0]["ir"].spec == r["ir"].spec
