@@ -1,35 +1,44 @@
 // brs_kernels.cuh -- sm_100a kernels of the batched World.step engine.
 //
 // One persistent CTA steps a TILE of TW consecutive worlds at a time; tiles are
-// handed out by a global atomic counter (dynamic scheduling, no tail).  Every
+// handed out by a global atomic counter (dynamic scheduling, self-resetting).  Every
 // phase of World.step runs data-parallel over the whole tile, so barriers and
 // per-world set-up are amortised over TW worlds and all threads work in every
-// phase whatever the shape of a single world:
+// phase whatever the shape of a single world.  The CTA is warp-specialised:
 //
-//   0. TMA     the tile's wall store (SoA rows x1|y1|x2|y2|rgba, TW*20*cap
-//              contiguous bytes) lands in shared memory through ONE bulk copy
-//              (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered and
-//              issued one tile ahead;
-//   1. PREP    thread per (world, robot): FP64 pose proposal, committed and
-//              proposed box corners; all threads: FP32 segment table;
-//   2. COLLIDE thread per (world, robot, wall): conservative FP32 disc cull, then
-//              the exact FP64 4-edge test (IEEE ops, no FMA contraction:
-//              decisions equal the float64 reference's); robot-vs-robot pairs
-//              in both orders so that the list-order dependence of Robot.step
-//              reduces to bit masks;
-//   3. COMMIT  thread per (world, robot): resolve the masks in list order, commit
-//              or stall, write pose / velocity / stalled;
-//   4. TABLE   rays that share an origin (all columns of a Camera, range sensors
-//              on one mount) get a per-(origin, segment) table m = n/na, q = d/na
-//              that makes the inner test division free:
-//                  1/t = m . r      u/t = r x q      hit: 0 <= u/t <= 1/t, 1/t >= 1
-//   5. SENSE   thread per ray (or SL lanes per ray when a tile has few rays):
-//              FP32 nearest-hit search (4 FP32 + 2 compares + 2 selects per test),
-//              warp-shuffle reduction over the SL lanes, then ONE FP64 refinement
-//              of the winning segment so distances and pixel rounding follow the
-//              float64 reference;
-//   6. PAINT   Camera.take_picture: the tile's pictures are one contiguous HBM
-//              block, written with coalesced 16-byte (4 x uchar4) streaming stores.
+//   HELPER team (threads >= NW): Robot.step of tile n+1
+//     TMA     the tile's wall store (SoA rows x1|y1|x2|y2|rgba, TW*20*cap contiguous
+//             bytes) lands in shared memory through ONE bulk copy (cp.async.bulk +
+//             mbarrier, SASS UBLKCP), double buffered.  Worlds too large for that
+//             ("big" shape) are read once from L2/HBM with 16-byte loads instead.
+//     PREP    thread per (world, robot): FP64 pose proposal, committed and proposed
+//             box corners; all helper threads: FP32 segment table;
+//     COLLIDE threads per (world, robot, wall): conservative FP32 disc cull, FP32 edge
+//             classifier with an explicit error bound, then the exact FP64 4-edge test
+//             (IEEE ops, no FMA contraction: decisions equal the float64 reference's);
+//             robot-vs-robot pairs in both orders so that the list-order dependence of
+//             Robot.step reduces to bit masks;
+//     COMMIT  thread per (world, robot): resolve the masks in list order, commit or
+//             stall, write pose / velocity / stalled, publish the box as search
+//             segments and the origins / cones of the robot's ray groups.
+//
+//   WORKER team (threads < NW): sensors and pictures of tile n
+//     TABLE   rays that share an origin (all columns of a Camera, range sensors on one
+//             mount) get a per-(origin, segment) table m = n/na, q = d/na that makes
+//             the inner test division free:
+//                 1/t = m . r      u/t = r x q      hit: 0 <= u/t <= 1/t, 1/t >= 1
+//             entries no ray of the group can reach (range, cone) are culled and the
+//             survivors compacted in index order;
+//     SENSE   thread per ray (or SL lanes per ray when a tile has few rays): FP32
+//             nearest-hit search (4 FP32 + 2 compares + 2 selects per test), warp-
+//             shuffle reduction over the SL lanes, then ONE FP64 refinement of the
+//             winning segment so distances and pixel rounding follow the float64
+//             reference;
+//     PAINT   Camera.take_picture: the tile's pictures are one contiguous HBM block,
+//             written with coalesced 16-byte (4 x uchar4) streaming stores.
+//
+// The teams meet once per tile (__syncthreads); inside a team, phases are separated by
+// named barriers.  Everything the helper hands to the workers is double buffered.
 //
 // Tensor cores are unused on purpose: the work is FP32 cross products with no
 // dense contraction (BASELINE.json north_star).
