@@ -57,7 +57,7 @@ struct brs_engine {
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
   int gtasks = 0, dtasks = 0;
-  bool big = false;
+  bool big = false, direct_on_helper = false;
   const void* kfn = nullptr;
 };
 
@@ -410,6 +410,12 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     const double helper_w = R * (cfg->seg_cap * 40.0 + 1500.0);
     const double worker_w = grp_rays * S * 6.0 + dir_rays * S * 17.0 + (grays + rrays + lrays) * 250.0 +
                             e->n_group * S * 45.0 + (double)ncols * e->cam_h * 1.5;
+    // camera worlds with a few direct-path sensors: the (otherwise mostly idle) helper team
+    // runs those sensors; per-warp it must stay clearly lighter than the workers
+    const double direct_w = dir_rays * S * 17.0 + (cfg->n_light + cfg->n_smell + e->n_dr) * 250.0;
+    e->direct_on_helper = ncols > 0 && dtasks > 0 &&
+                          (helper_w + direct_w) * (T_total / 32 - 1) < 0.6 * (worker_w - direct_w);
+    e->direct_on_helper = env_int("BRS_DIRECT_ON_HELPER", e->direct_on_helper ? 1 : 0) != 0 && dtasks > 0;
     int nh = (int)std::lround(T_total / 32.0 * helper_w / (helper_w + worker_w));
     nh = std::max(1, std::min(nh, T_total / 32 - 1));
     nh = env_int("BRS_NH", nh);
@@ -451,8 +457,9 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->T = e->NW + 32 * e->NH;
   e->GS = std::min(32 * e->NH, std::max(8, pow2ceil(cfg->seg_cap)));  // helper threads per (world, robot)
   e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * tw), 1))) : 1;
-  e->SLD = e->n_dr ? std::min(32, pow2floor(std::max(e->NW / (e->n_dr * tw), 1))) : 1;
-  e->SLL = cfg->n_light ? std::min(32, pow2floor(std::max(e->NW / (cfg->n_light * tw), 1))) : 1;
+  const int dteam = e->direct_on_helper ? 32 * e->NH : e->NW;  // threads that run the direct path
+  e->SLD = e->n_dr ? std::min(32, pow2floor(std::max(dteam / (e->n_dr * tw), 1))) : 1;
+  e->SLL = cfg->n_light ? std::min(32, pow2floor(std::max(dteam / (cfg->n_light * tw), 1))) : 1;
   {
     const int Q = std::max(e->cam_w / 4, 1);
     const int slots = std::max(e->NW / std::min(Q, e->NW), 1);
@@ -557,6 +564,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
   p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.SLL = e->SLL; p.paint_rs = e->paint_rs;
   p.flat_rows = e->flat_rows;
+  p.direct_on_helper = e->direct_on_helper ? 1 : 0;
   p.fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
   p.NW = e->NW; p.NH = e->NH;
   {

@@ -121,6 +121,7 @@ struct KParams {
   int SLG, SLD, SLL; // lanes per ray task: group path, direct range path, light path (powers of two <= 32)
   int n_gr, n_dr;    // range sensors on the group path / on the direct path
   int paint_rs;      // row slots of the paint phase
+  int direct_on_helper;  // the helper team runs the direct-path sensors (camera worlds with few of them)
   int fused_table;   // TABLE phase: one warp per (world, group) builds and compacts in one pass
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
@@ -671,10 +672,120 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
   }
 }
 
+// Direct-path sensors of one tile -- range sensors on their own mount, light sensors,
+// smell sensors -- run by a team of `tn` threads (index tt).  One homogeneous loop per
+// device kind: mixing kinds in a warp would serialise their code paths.  Either team can
+// run this: the workers for sensor-heavy worlds, the otherwise idle helper team for
+// camera worlds with a few extra sensors (right after it committed the tile's poses).
+__device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, int lane, int w0, int nw,
+                                             const uint32_t* __restrict__ rawb, const float4* __restrict__ segtab,
+                                             const double* __restrict__ wsb, const int2* __restrict__ meta) {
+  const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
+  // range sensors on their own mount ...
+  if (p.n_dr > 0) {
+    const int SL = p.SLD, g = tt & (SL - 1), slot = tt / SL, nslot = tn / SL;
+    const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
+    const int ntask = p.n_dr;
+    for (int i = slot; i < nw * ntask; i += nslot) {
+      const int wl = (int)fdiv(i, p.dDT), task = i - wl * ntask, w = w0 + wl;
+      const int S = meta[wl].x, nseg = S + 4 * R;
+      const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+      const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+      const float4* st = segtab + (size_t)wl * nvis;
+      // RangeSensor.update
+      const int si = p.dr_idx[task];
+      const RangeDev& sd = p.ranges[si];
+      const int r = sd.robot;
+      double x1, y1, ca, sa;
+      mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
+      const float ox = (float)x1, oy = (float)y1;
+      const int own_lo = S + 4 * r, own_hi = own_lo + 4;
+      double best = sd.max;  // the reading stays at max unless a ray hits nearer
+      for (int k = 0; k < sd.n_rays; ++k) {
+        const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
+        const double dyu = da(dm(sa, sd.cr[k]), dm(ca, sd.sr[k]));
+        const double x2 = da(dm(dxu, sd.max), x1), y2 = da(dm(dyu, sd.max), y1);
+        const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
+        uint32_t key = BRS_KEY_NOHIT;
+        int idx = -1;
+        if (SL == 1) {
+          search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
+          search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
+        } else {
+          search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+          search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+          group_min(key, idx, SL, gmask);
+        }
+        if (g == 0 && idx >= 0) best = fmin(best, refine64(raw, SC, S, ws, idx, x1, y1, x2, y2, sd.max));
+      }
+      // (upstream stores reading = d / max and returns reading * max: the float32
+      //  observation cannot see that round trip)
+      if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
+    }
+  }
+  // ... light sensors: line of sight to every bulb ...
+  if (p.n_light > 0) {
+    const int SL = p.SLL, g = tt & (SL - 1), slot = tt / SL, nslot = tn / SL;
+    const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
+    const int ntask = p.n_light;
+    for (int i = slot; i < nw * ntask; i += nslot) {
+      const int wl = (int)fdiv(i, p.dLT), li = i - wl * ntask, w = w0 + wl;
+      const int S = meta[wl].x, nseg = S + 4 * R;
+      const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+      const float4* st = segtab + (size_t)wl * nvis;
+      const PointDev& sd = p.lights[li];
+      const int r = sd.robot;
+      double x1, y1, ca, sa;
+      mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
+      const float ox = (float)x1, oy = (float)y1;
+      const int own_lo = S + 4 * r, own_hi = own_lo + 4;
+      double value = 0.0;
+      for (int b = 0; b < p.n_bulbs; ++b) {
+        const float* bl = p.bulbs + ((size_t)w * p.n_bulbs + b) * 4;
+        const double bx = (double)bl[0], by = (double)bl[1], br = (double)bl[3];
+        const double ex = ds(bx, x1), ey = ds(by, y1);
+        const double dist = sqrt(da(dm(ex, ex), dm(ey, ey)));
+        const float rx = (float)ex, ry = (float)ey;
+        uint32_t key = BRS_KEY_NOHIT;
+        int idx = -1;
+        if (SL == 1) {
+          search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
+          search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
+        } else {
+          search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
+          search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
+          group_min(key, idx, SL, gmask);
+        }
+        if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
+      }
+      if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
+    }
+  }
+  // ... smell sensors: grid lookup at the mount point
+  if (p.n_smell > 0) {
+    const int ntask = p.n_smell;
+    for (int i = tt; i < nw * ntask; i += tn) {
+      const int wl = (int)fdiv(i, p.dST), si = i - wl * ntask, w = w0 + wl;
+      const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
+      const PointDev& sd = p.smells[si];
+      double x1, y1, ca, sa;
+      mount_point(ws + sd.robot * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
+      float v = 0.f;
+      if (p.grid_w > 0) {
+        const int gx = (int)(x1 / p.smell_cell), gy = (int)(y1 / p.smell_cell);
+        if (gx >= 0 && gx < p.grid_w && gy >= 0 && gy < p.grid_h)
+          v = p.grid[((size_t)w * p.grid_h + gy) * p.grid_w + gx];
+      }
+      p.smell_out[(size_t)w * p.n_smell + si] = v;
+    }
+  }
+
+}
+
 // Robot.step of one tile by the helper team (thread ht of nth): PREP, then the
 // collision tests, then commit / stall and everything that hangs off the final pose.
 __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
-                                                bool do_rays, const uint32_t* __restrict__ rawb,
+                                                bool do_rays, bool do_sense, const uint32_t* __restrict__ rawb,
                                                 float4* __restrict__ segtab, double* __restrict__ wsb,
                                                 int4* __restrict__ cflag, int2* __restrict__ meta,
                                                 double2* __restrict__ org, GroupCull* __restrict__ gcull, uint32_t bar,
@@ -853,6 +964,12 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
         }
       }
     }
+  // camera worlds with a few extra sensors: the helper team has time to spare, the workers
+  // do not -- run the direct-path sensors of this tile here, on the poses just committed
+  if (do_sense && p.direct_on_helper) {
+    team_sync(2, nth);
+    sense_direct(p, ht, nth, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta);
+  }
 }
 
 template <int NR, bool BIG>
@@ -929,7 +1046,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         // big worlds (one or two CTAs per SM by their tables alone) do not stage the wall
         // store: the helper reads it once from L2 / HBM, coalesced, to build the FP32 table
         const uint32_t* rawn = BIG ? p.seg + (size_t)wn * 5 * SC : (const uint32_t*)(smem + L.raw[buf ^ 1]);
-        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, rawn,
+        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, do_sense, rawn,
                         (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
                         (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
                         (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
@@ -1113,105 +1230,8 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
           }
         }
       }
-      // 5b. direct path, one homogeneous loop per device kind (mixing kinds in a warp would
-      //     serialise their code paths): range sensors on their own mount, ...
-      if (do_sense && p.n_dr > 0) {
-        const int SL = p.SLD, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
-        const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
-        const int ntask = p.n_dr;
-        for (int i = slot; i < nw * ntask; i += nslot) {
-          const int wl = (int)fdiv(i, p.dDT), task = i - wl * ntask, w = w0 + wl;
-          const int S = meta[wl].x, nseg = S + 4 * R;
-          const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
-          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
-          const float4* st = segtab + (size_t)wl * nvis;
-          // RangeSensor.update
-          const int si = p.dr_idx[task];
-          const RangeDev& sd = p.ranges[si];
-          const int r = sd.robot;
-          double x1, y1, ca, sa;
-          mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
-          const float ox = (float)x1, oy = (float)y1;
-          const int own_lo = S + 4 * r, own_hi = own_lo + 4;
-          double best = sd.max;  // the reading stays at max unless a ray hits nearer
-          for (int k = 0; k < sd.n_rays; ++k) {
-            const double dxu = ds(dm(ca, sd.cr[k]), dm(sa, sd.sr[k]));
-            const double dyu = da(dm(sa, sd.cr[k]), dm(ca, sd.sr[k]));
-            const double x2 = da(dm(dxu, sd.max), x1), y2 = da(dm(dyu, sd.max), y1);
-            const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
-            uint32_t key = BRS_KEY_NOHIT;
-            int idx = -1;
-            if (SL == 1) {
-              search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
-              search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
-            } else {
-              search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-              search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-              group_min(key, idx, SL, gmask);
-            }
-            if (g == 0 && idx >= 0) best = fmin(best, refine64(raw, SC, S, ws, idx, x1, y1, x2, y2, sd.max));
-          }
-          // (upstream stores reading = d / max and returns reading * max: the float32
-          //  observation cannot see that round trip)
-          if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
-        }
-      }
-      // ... light sensors: line of sight to every bulb ...
-      if (do_sense && p.n_light > 0) {
-        const int SL = p.SLL, g = tid & (SL - 1), slot = tid / SL, nslot = NW / SL;
-        const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
-        const int ntask = p.n_light;
-        for (int i = slot; i < nw * ntask; i += nslot) {
-          const int wl = (int)fdiv(i, p.dLT), li = i - wl * ntask, w = w0 + wl;
-          const int S = meta[wl].x, nseg = S + 4 * R;
-          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
-          const float4* st = segtab + (size_t)wl * nvis;
-          const PointDev& sd = p.lights[li];
-          const int r = sd.robot;
-          double x1, y1, ca, sa;
-          mount_point(ws + r * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
-          const float ox = (float)x1, oy = (float)y1;
-          const int own_lo = S + 4 * r, own_hi = own_lo + 4;
-          double value = 0.0;
-          for (int b = 0; b < p.n_bulbs; ++b) {
-            const float* bl = p.bulbs + ((size_t)w * p.n_bulbs + b) * 4;
-            const double bx = (double)bl[0], by = (double)bl[1], br = (double)bl[3];
-            const double ex = ds(bx, x1), ey = ds(by, y1);
-            const double dist = sqrt(da(dm(ex, ex), dm(ey, ey)));
-            const float rx = (float)ex, ry = (float)ey;
-            uint32_t key = BRS_KEY_NOHIT;
-            int idx = -1;
-            if (SL == 1) {
-              search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
-              search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
-            } else {
-              search_direct<false>(st, 0, own_lo, g, SL, ox, oy, rx, ry, key, idx);
-              search_direct<false>(st, own_hi, nseg, g, SL, ox, oy, rx, ry, key, idx);
-              group_min(key, idx, SL, gmask);
-            }
-            if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
-          }
-          if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
-        }
-      }
-      // ... smell sensors: grid lookup at the mount point
-      if (do_sense && p.n_smell > 0) {
-        const int ntask = p.n_smell;
-        for (int i = tid; i < nw * ntask; i += NW) {
-          const int wl = (int)fdiv(i, p.dST), si = i - wl * ntask, w = w0 + wl;
-          const double* ws = wsb + (size_t)wl * R * BRS_WS_STRIDE;
-          const PointDev& sd = p.smells[si];
-          double x1, y1, ca, sa;
-          mount_point(ws + sd.robot * BRS_WS_STRIDE, sd.mx, sd.my, x1, y1, ca, sa);
-          float v = 0.f;
-          if (p.grid_w > 0) {
-            const int gx = (int)(x1 / p.smell_cell), gy = (int)(y1 / p.smell_cell);
-            if (gx >= 0 && gx < p.grid_w && gy >= 0 && gy < p.grid_h)
-              v = p.grid[((size_t)w * p.grid_h + gy) * p.grid_w + gx];
-          }
-          p.smell_out[(size_t)w * p.n_smell + si] = v;
-        }
-      }
+      // 5b. direct path (unless the helper team already ran it for this tile)
+      if (do_sense && !p.direct_on_helper) sense_direct(p, tid, NW, lane, w0, nw, rawb, segtab, wsb, meta);
 
       // ---------------- PAINT ----------------------------------------------------------------
       if (do_cam) {

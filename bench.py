@@ -266,7 +266,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eng.step(flags=flags, stream=sh)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("BRS_BENCH_NO_CLOCKS") else None
     if sampler:
         sampler.start()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]

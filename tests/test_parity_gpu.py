@@ -180,7 +180,8 @@ def test_culling_and_tiling_never_change_results(maker):
     scene = maker()
     base = _outputs(scene, 3, {})
     for env in ({"BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_TW": "1"}, {"BRS_TW": "5", "BRS_BIG": "1"},
-                {"BRS_NH": "2"}, {"BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
+                {"BRS_NH": "2"}, {"BRS_DIRECT_ON_HELPER": "1"}, {"BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
+                {"BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
         other = _outputs(scene, 3, env)
         for k in base:
             if k in ("range", "light") and env.get("BRS_GROUP_MIN"):
