@@ -20,6 +20,9 @@
  *     brs_bind_output() redirects an observation buffer to caller memory, e.g.
  *     a slice of an NCCL all-gather buffer.
  *   - there is no CPU fallback: without a CUDA device brs_create() fails.
+ *   - an engine steps one launch at a time: brs_step calls on one engine must be
+ *     ordered (same stream, or events between streams); different engines are
+ *     independent.
  *
  * Angles are radians, lengths are world units (cm upstream), y grows downward.
  */
@@ -155,7 +158,10 @@ int brs_download(brs_engine* e, int which, void* host, int first_world, int n_wo
 
 /* World.step(time_step) over every world of the engine: one fused kernel
  * launch (upstream world.py: World.step -> robot.py: Robot.step, Robot.update
- * -> devices/*.update; cameras.py: Camera.take_picture when BRS_STEP_CAMERA). */
+ * -> devices/*.update; cameras.py: Camera.take_picture when BRS_STEP_CAMERA).
+ * RangeSensor observations are the float32 rounding of the float64 hit distance
+ * (upstream keeps reading = d / max and returns reading * max; float32 cannot
+ * see that round trip). */
 int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
 
 /* Same step driven with HOST buffers (the end-to-end path): copies target
