@@ -182,7 +182,7 @@ struct __align__(16) Strip {
 
 // shared memory carve-up, byte offsets; mirrored on the host for the launch size
 struct SmemLayout {
-  int raw[2], segtab[2], gtab, gidx, gcnt, gcull[2], ws[2], org[2], cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, mbar, sched, total;
+  int raw[2], segtab[2], gtab, gidx, gcnt, gcull[2], ws[2], org[2], cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, cq, mbar, sched, total;
 };
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, int n_group, int n_camera, int cam_w,
@@ -207,7 +207,8 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   L.camcs = o; o += n_camera * cam_w * 16;
   L.rowsky = o; o += cam_h * 4;
   L.rowgnd = o; o += cam_h * 4;
-  o = align_up(o, 8);
+  o = align_up(o, 16);
+  L.cq = o; o += 4 * 256;  // collision candidate queue: count + BRS_CQ_MAX packed (robot item, wall)
   L.mbar = o; o += 2 * 8;
   L.sched = o; o += 16;
   L.total = align_up(o, 16);
@@ -589,6 +590,48 @@ __device__ __forceinline__ void team_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Proposed box of robot item i (= world wl, slot r) against wall j: FP32 classification of
+// the 4 edges against the wall widened by an explicit error bound, then the exact float64
+// 4-edge test for what is not a certain miss.
+#define BRS_CQ_MAX 252
+__device__ __forceinline__ bool box_hits_wall(const KParams& p, const double* __restrict__ wsb,
+                                              const uint32_t* __restrict__ rawb, const float4* __restrict__ st, int i,
+                                              int j, int wl, int r, int SC) {
+  const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
+  const float cx = (float)pr[8], cy = (float)pr[9];
+  const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
+  const float cscale = 4e-7f * (fabsf(cx) + fabsf(cy) + rad + 1.f);
+  const float4 s = st[j];
+  bool maybe = false;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int e2 = (e + 1) & 3;
+    const float pcx = (float)pr[2 * e], pcy = (float)pr[2 * e + 1];
+    const float pex = (float)(pr[2 * e2] - pr[2 * e]), pey = (float)(pr[2 * e2 + 1] - pr[2 * e + 1]);
+    const float bx = pcx - s.x, by = pcy - s.y;  // edge start relative to the wall start
+    const float den = s.w * pex - s.z * pey;
+    const float na = s.z * by - s.w * bx, nb = pex * by - pey * bx;
+    // error bound: coordinates carry ~6e-8 * |coordinate| of FP32 rounding, which the
+    // cross products scale by the edge / wall lengths; products add ~1e-7 relative
+    const float ad = fabsf(den);
+    const float tol = cscale * (fabsf(s.z) + fabsf(s.w) + fabsf(pex) + fabsf(pey)) + 1e-5f * (fabsf(na) + fabsf(nb) + ad);
+    const float sa_ = den < 0.f ? -na : na, sb_ = den < 0.f ? -nb : nb;
+    maybe |= !(sa_ < -tol || sa_ > ad + tol || sb_ < -tol || sb_ > ad + tol);
+  }
+  if (!maybe) return false;
+  const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+  const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
+  const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
+  bool hit = false;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int e2 = (e + 1) & 3;
+    hit |= isect64_bool(pr[2 * e], pr[2 * e + 1], ds(pr[2 * e2], pr[2 * e]), ds(pr[2 * e2 + 1], pr[2 * e + 1]), x3, y3,
+                        x4, y4);
+  }
+  return hit;
+}
+
 // PREP of one tile, run by `nth` helper threads (index ht): robot state HBM ->
 // shared, heading trig, proposed pose and velocity, committed and proposed box
 // corners (compute_boundingbox), collision flags cleared, per-world meta and the
@@ -598,53 +641,58 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
                                              double* __restrict__ wsb, int4* __restrict__ cflag,
                                              int2* __restrict__ meta, uint32_t bar, uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
-  for (int i = ht; i < nw * R; i += nth) {
+  // Each robot is two independent halves on two lanes -- the committed pose (heading trig,
+  // box corners) and the proposal (velocity ramp, proposed pose, its trig and corners) --
+  // written branch-free around ONE sincos call, so the float64 dependency chain of PREP is
+  // half as long and twice as many lanes work.
+  const int nhalf = do_move ? 2 : 1;
+  for (int h = ht; h < nw * R * nhalf; h += nth) {
+    const int i = do_move ? (h >> 1) : h;
+    const bool prop = do_move && (h & 1);
     const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
     const RobotDev& rd = p.robots[r];
     double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
     const size_t o = ((size_t)w * R + r) * 3;
     const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
     const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
-    wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
-    wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
-    double s0, c0;
-    sincos(a, &s0, &c0);
-    wsr[BRS_WS_RCS] = c0;
-    wsr[BRS_WS_RCS + 1] = s0;
-    double px = x, py = y, c1 = c0, s1 = s0;
-    double* pr = wsr + BRS_WS_PROP;
-    if (do_move) {
+    double vx = v0, vy = v1, va = v2, pa = a;
+    if (prop) {
       const double* tv = p.tvel + o;
-      const double vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
-      const double vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
-      const double va = deltav(tv[2], v2, rd.va_ramp, p.dt);
-      const double pa = ds(a, dm(va, p.dt));
-      const double ang = da(-pa, BRS_PI_OVER_2);
-      double sn, cs;
-      sincos(ang, &sn, &cs);
-      // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
-      const double tvx = da(dm(vx, sn), dm(dm(vy, cs), p.dt));
-      const double tvy = ds(dm(vx, cs), dm(dm(vy, sn), p.dt));
-      px = da(x, tvx);
-      py = da(y, tvy);
-      c1 = sn;  // sin(pi/2 - pa) = cos(pa)
-      s1 = cs;  // cos(pi/2 - pa) = sin(pa)
-      pr[8] = px; pr[9] = py; pr[10] = pa;
-      pr[11] = vx; pr[12] = vy; pr[13] = va;
-      pr[14] = c1; pr[15] = s1;
+      vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
+      vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
+      va = deltav(tv[2], v2, rd.va_ramp, p.dt);
+      pa = ds(a, dm(va, p.dt));
     }
+    double sn, cs;
+    sincos(prop ? da(-pa, BRS_PI_OVER_2) : a, &sn, &cs);
+    // heading cos / sin of this half: (cos a, sin a), or (cos pa, sin pa) = (sin, cos)(pi/2 - pa)
+    const double c = prop ? sn : cs, sgn = prop ? cs : sn;
+    double px = x, py = y;
+    if (prop) {
+      // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
+      px = da(x, da(dm(vx, sn), dm(dm(vy, cs), p.dt)));
+      py = da(y, ds(dm(vx, cs), dm(dm(vy, sn), p.dt)));
+    }
+    double* box = wsr + (prop ? BRS_WS_PROP : BRS_WS_DBOX);
     // corner = centre + R(heading) * (corner offset in the a=0 frame)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const double ox = rd.cox[k], oy = rd.coy[k];
-      wsr[BRS_WS_DBOX + 2 * k] = da(x, ds(dm(c0, ox), dm(s0, oy)));
-      wsr[BRS_WS_DBOX + 2 * k + 1] = da(y, da(dm(s0, ox), dm(c0, oy)));
-      if (do_move) {
-        pr[2 * k] = da(px, ds(dm(c1, ox), dm(s1, oy)));
-        pr[2 * k + 1] = da(py, da(dm(s1, ox), dm(c1, oy)));
-      }
+      box[2 * k] = da(px, ds(dm(c, ox), dm(sgn, oy)));
+      box[2 * k + 1] = da(py, da(dm(sgn, ox), dm(c, oy)));
     }
-    cflag[i] = make_int4(0, 0, 0, 0);
+    if (prop) {
+      double* pr = wsr + BRS_WS_PROP;
+      pr[8] = px; pr[9] = py; pr[10] = pa;
+      pr[11] = vx; pr[12] = vy; pr[13] = va;
+      pr[14] = c; pr[15] = sgn;
+    } else {
+      wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
+      wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
+      wsr[BRS_WS_RCS] = c;
+      wsr[BRS_WS_RCS + 1] = sgn;
+      cflag[i] = make_int4(0, 0, 0, 0);
+    }
   }
   for (int wl = ht; wl < nw; wl += nth) {
     const int w = w0 + wl;
@@ -788,9 +836,10 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
                                                 bool do_rays, bool do_sense, const uint32_t* __restrict__ rawb,
                                                 float4* __restrict__ segtab, double* __restrict__ wsb,
                                                 int4* __restrict__ cflag, int2* __restrict__ meta,
-                                                double2* __restrict__ org, GroupCull* __restrict__ gcull, uint32_t bar,
-                                                uint32_t parity, bool staged) {
+                                                double2* __restrict__ org, GroupCull* __restrict__ gcull,
+                                                int* __restrict__ cq, uint32_t bar, uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
+  if (ht == 0) cq[0] = 0;  // candidate queue of the collision phase
   prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, bar, parity, staged);
   team_sync(2, nth);
   if (do_move) {
@@ -799,6 +848,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
     // (distance of the proposed centre to the segment vs the box circumradius plus a
     // margin far above FP32 error), an FP32 classification of the 4 edges, then the
     // exact FP64 4-edge test for what is not a certain miss.
+      // pass 1: the cull, branch-free per wall; what falls inside a disc goes to a queue
       {
         const int GS = min(p.GS, nth), gi = ht / GS, gl = ht - gi * GS, ngrp = nth / GS;
         if (gi < ngrp) {
@@ -809,18 +859,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
             const float cx = (float)pr[8], cy = (float)pr[9];
             const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
             const float rad2 = rad * rad;
-            const float cscale = 4e-7f * (fabsf(cx) + fabsf(cy) + rad + 1.f);
             const float4* st = segtab + (size_t)wl * nvis;
-            float pc[8], pe[8];  // proposed corners and edge vectors, FP32
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int e2 = (e + 1) & 3;
-              pc[2 * e] = (float)pr[2 * e];
-              pc[2 * e + 1] = (float)pr[2 * e + 1];
-              pe[2 * e] = (float)(pr[2 * e2] - pr[2 * e]);
-              pe[2 * e + 1] = (float)(pr[2 * e2 + 1] - pr[2 * e + 1]);
-            }
-            bool hit = false;
             for (int j = gl; j < S; j += GS) {
               const float4 s = st[j];
               const float ax = cx - s.x, ay = cy - s.y;
@@ -829,38 +868,25 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
               h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
               const float vx = fmaf(-h, s.z, ax), vy = fmaf(-h, s.w, ay);
               if (fmaf(vx, vx, vy * vy) <= rad2) {
-                // inside the disc: classify the 4 edges in FP32 against the segment widened
-                // by a margin far above FP32 error; only an edge that is not a certain miss
-                // pays for the exact FP64 test
-                bool maybe = false;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float bx = pc[2 * e] - s.x, by = pc[2 * e + 1] - s.y;  // edge start relative to the wall start
-                  const float den = s.w * pe[2 * e] - s.z * pe[2 * e + 1];
-                  const float na = s.z * by - s.w * bx, nb = pe[2 * e] * by - pe[2 * e + 1] * bx;
-                  // error bound: coordinates carry ~6e-8 * |coordinate| of FP32 rounding, which the
-                  // cross products scale by the edge / wall lengths; products add ~1e-7 relative
-                  const float ad = fabsf(den);
-                  const float tol = cscale * (fabsf(s.z) + fabsf(s.w) + fabsf(pe[2 * e]) + fabsf(pe[2 * e + 1])) +
-                                    1e-5f * (fabsf(na) + fabsf(nb) + ad);
-                  const float sa_ = den < 0.f ? -na : na, sb_ = den < 0.f ? -nb : nb;
-                  maybe |= !(sa_ < -tol || sa_ > ad + tol || sb_ < -tol || sb_ > ad + tol);
-                }
-                if (maybe) {
-                  const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
-                  const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
-                  const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int e2 = (e + 1) & 3;
-                    hit |= isect64_bool(pr[2 * e], pr[2 * e + 1], ds(pr[2 * e2], pr[2 * e]),
-                                        ds(pr[2 * e2 + 1], pr[2 * e + 1]), x3, y3, x4, y4);
-                  }
-                }
+                const int pos = atomicAdd(&cq[0], 1);
+                if (pos < BRS_CQ_MAX)
+                  cq[4 + pos] = (i << 16) | j;
+                else if (box_hits_wall(p, wsb, rawb, st, i, j, wl, r, SC))  // queue full: test in place
+                  cflag[i].x = 1;
               }
             }
-            if (hit) cflag[i].x = 1;
           }
+        }
+      }
+      team_sync(2, nth);
+      // pass 2: the queued (robot, wall) pairs, one per thread: FP32 edge classifier, then the
+      // exact FP64 test for what is not a certain miss
+      {
+        const int n = min(cq[0], BRS_CQ_MAX);
+        for (int c = ht; c < n; c += nth) {
+          const int e = cq[4 + c], i = e >> 16, j = e & 0xffff;
+          const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
+          if (box_hits_wall(p, wsb, rawb, segtab + (size_t)wl * nvis, i, j, wl, r, SC)) cflag[i].x = 1;
         }
       }
     // robots: proposal i against the committed box of o (pair_old) and, for o < i,
@@ -1050,7 +1076,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
                         (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
                         (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
                         (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
-                        smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
+                        (int*)(smem + L.cq), smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
       }
     } else if (do_rays && it >= 0) {
       // ================= workers: sensors and pictures of THIS tile ====================
