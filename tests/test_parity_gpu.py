@@ -368,3 +368,32 @@ def test_random_scenes_match_the_oracle():
         parity.compare(scene, n_steps=3)
 
     run()
+
+
+def test_very_wide_camera_and_sky_gradient():
+    """Pictures wider than 4 x the worker count (several column quads per thread) and the
+    non-flat sky / ground rows (generic paint loop)."""
+    from oracle import aitk_oracle as orc
+    from oracle import scene_adapter as sa
+
+    scene = rb.scenes.config2(n_worlds=6, cam_w=640, cam_h=9)
+    stats = parity.compare(scene, n_steps=2)
+    assert stats["pixel_mismatch"] <= 0.002 * stats["pixels"]
+    # vertical gradients: colour = base + grad * |j - H/2| / (H/2)
+    scene = rb.scenes.config2(n_worlds=4, cam_w=64, cam_h=32)
+    sky_grad, gnd_grad = (40, 20, 100), (30, 60, 10)
+    old = (orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD)
+    orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD = sky_grad, gnd_grad
+    try:
+        eng = rb.BatchEngine(scene, sky_grad=sky_grad, ground_grad=gnd_grad)
+        eng.step()
+        eng.synchronize()
+        cam = eng.download("camera")
+        eng.close()
+        for i in range(4):
+            ref = np.array(sa.step_and_observe(scene, i, 1)["camera"][0], dtype=np.uint8)
+            diff = np.any(cam[i, 0] != ref, axis=2)
+            assert diff.any(axis=0).sum() <= 1, i
+        assert len(np.unique(cam[0, 0, :3, :, 2])) > 1  # the sky really is a gradient
+    finally:
+        orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD = old
