@@ -28,3 +28,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """libbrs.so is built in-tree (it travels with the snapshot); build it if it is missing or
+    older than its sources so that no test ever runs against a stale binary."""
+    import __graft_entry__ as ge
+
+    ge.build()
+    yield
