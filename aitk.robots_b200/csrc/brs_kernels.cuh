@@ -182,7 +182,7 @@ struct __align__(16) Strip {
 
 // shared memory carve-up, byte offsets; mirrored on the host for the launch size
 struct SmemLayout {
-  int raw[2], segtab[2], gtab, gidx, gcnt, gcull[2], ws[2], org[2], cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, cq, mbar, sched, total;
+  int raw[2], segtab[2], gtab, gidx, gcnt, gcull[2], ws[2], org[2], cflag[2], meta[2], colinfo, strips, camcs, rowsky, rowgnd, cq, cpar, mbar, sched, total;
 };
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, int n_group, int n_camera, int cam_w,
@@ -208,6 +208,7 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   L.rowsky = o; o += cam_h * 4;
   L.rowgnd = o; o += cam_h * 4;
   o = align_up(o, 16);
+  L.cpar = o; o += TW * R * 16;  // collision disc per (world, robot): centre, radius^2 (helper-only, transient)
   L.cq = o; o += 4 * 256;  // collision candidate queue: count + BRS_CQ_MAX packed (robot item, wall)
   L.mbar = o; o += 2 * 8;
   L.sched = o; o += 16;
@@ -639,8 +640,15 @@ __device__ __forceinline__ bool box_hits_wall(const KParams& p, const double* __
 __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
                                              const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
                                              double* __restrict__ wsb, int4* __restrict__ cflag,
-                                             int2* __restrict__ meta, uint32_t bar, uint32_t parity, bool staged) {
+                                             int2* __restrict__ meta, float4* __restrict__ cpar, uint32_t bar,
+                                             uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
+  // per-world meta first: its global loads overlap the float64 chain below
+  for (int wl = ht; wl < nw; wl += nth) {
+    const int w = w0 + wl;
+    meta[wl].x = min(max(p.seg_count[w], 0), SC);
+    meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
+  }
   // Each robot is two independent halves on two lanes -- the committed pose (heading trig,
   // box corners) and the proposal (velocity ramp, proposed pose, its trig and corners) --
   // written branch-free around ONE sincos call, so the float64 dependency chain of PREP is
@@ -686,6 +694,10 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
       pr[8] = px; pr[9] = py; pr[10] = pa;
       pr[11] = vx; pr[12] = vy; pr[13] = va;
       pr[14] = c; pr[15] = sgn;
+      // FP32 disc of the cull: proposed centre, (circumradius + margin)^2
+      const float cxf = (float)px, cyf = (float)py;
+      const float rad = (float)rd.radius + p.cull_margin + 1e-5f * (fabsf(cxf) + fabsf(cyf));
+      cpar[i] = make_float4(cxf, cyf, rad * rad, 0.f);
     } else {
       wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
       wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
@@ -693,11 +705,6 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
       wsr[BRS_WS_RCS + 1] = sgn;
       cflag[i] = make_int4(0, 0, 0, 0);
     }
-  }
-  for (int wl = ht; wl < nw; wl += nth) {
-    const int w = w0 + wl;
-    meta[wl].x = min(max(p.seg_count[w], 0), SC);
-    meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
   }
   // the tile's wall store was requested before the robot state: by now it has usually landed
   if (staged) mbar_wait(bar, parity);
@@ -837,10 +844,11 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
                                                 float4* __restrict__ segtab, double* __restrict__ wsb,
                                                 int4* __restrict__ cflag, int2* __restrict__ meta,
                                                 double2* __restrict__ org, GroupCull* __restrict__ gcull,
-                                                int* __restrict__ cq, uint32_t bar, uint32_t parity, bool staged) {
+                                                int* __restrict__ cq, float4* __restrict__ cpar, uint32_t bar,
+                                                uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
   if (ht == 0) cq[0] = 0;  // candidate queue of the collision phase
-  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, bar, parity, staged);
+  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, cpar, bar, parity, staged);
   team_sync(2, nth);
   if (do_move) {
     // ---------------- COLLIDE ------------------------------------------------------
@@ -848,31 +856,41 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
     // (distance of the proposed centre to the segment vs the box circumradius plus a
     // margin far above FP32 error), an FP32 classification of the 4 edges, then the
     // exact FP64 4-edge test for what is not a certain miss.
-      // pass 1: the cull, branch-free per wall; what falls inside a disc goes to a queue
+      // pass 1: the cull, flat over (world, robot, wall) and four items per thread and step, so
+      // that four independent dependency chains are in flight (the helper team is latency
+      // bound); what falls inside a disc goes to a queue
       {
-        const int GS = min(p.GS, nth), gi = ht / GS, gl = ht - gi * GS, ngrp = nth / GS;
-        if (gi < ngrp) {
-          for (int i = gi; i < nw * R; i += ngrp) {
-            const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
-            const int S = meta[wl].x;
-            const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
-            const float cx = (float)pr[8], cy = (float)pr[9];
-            const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
-            const float rad2 = rad * rad;
-            const float4* st = segtab + (size_t)wl * nvis;
-            for (int j = gl; j < S; j += GS) {
-              const float4 s = st[j];
-              const float ax = cx - s.x, ay = cy - s.y;
-              const float ee = fmaf(s.z, s.z, s.w * s.w);
-              float h = fmaf(ax, s.z, ay * s.w) * rcp_approx(ee);
-              h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
-              const float vx = fmaf(-h, s.z, ax), vy = fmaf(-h, s.w, ay);
-              if (fmaf(vx, vx, vy * vy) <= rad2) {
-                const int pos = atomicAdd(&cq[0], 1);
-                if (pos < BRS_CQ_MAX)
-                  cq[4 + pos] = (i << 16) | j;
-                else if (box_hits_wall(p, wsb, rawb, st, i, j, wl, r, SC))  // queue full: test in place
-                  cflag[i].x = 1;
+        const int total = nw * R * SC;
+        for (int base = ht; base < total; base += 4 * nth) {
+          int it_i[4], it_j[4];
+          bool inside[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int item = base + k * nth;
+            const bool valid = item < total;
+            const int i = valid ? (int)fdiv(item, p.dSC) : 0, j = valid ? item - i * SC : 0;
+            const int wl = (int)fdiv(i, p.dR);
+            const float4 cp = cpar[i];
+            const float4 s = segtab[(size_t)wl * nvis + j];
+            const float ax = cp.x - s.x, ay = cp.y - s.y;
+            const float ee = fmaf(s.z, s.z, s.w * s.w);
+            float h = fmaf(ax, s.z, ay * s.w) * rcp_approx(ee);
+            h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
+            const float vx = fmaf(-h, s.z, ax), vy = fmaf(-h, s.w, ay);
+            inside[k] = valid && j < meta[wl].x && fmaf(vx, vx, vy * vy) <= cp.z;
+            it_i[k] = i;
+            it_j[k] = j;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (inside[k]) {
+              const int i = it_i[k], j = it_j[k];
+              const int pos = atomicAdd(&cq[0], 1);
+              if (pos < BRS_CQ_MAX) {
+                cq[4 + pos] = (i << 16) | j;
+              } else {  // queue full: test in place
+                const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
+                if (box_hits_wall(p, wsb, rawb, segtab + (size_t)wl * nvis, i, j, wl, r, SC)) cflag[i].x = 1;
               }
             }
           }
@@ -1076,7 +1094,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
                         (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
                         (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
                         (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
-                        (int*)(smem + L.cq), smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
+                        (int*)(smem + L.cq), (float4*)(smem + L.cpar), smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
       }
     } else if (do_rays && it >= 0) {
       // ================= workers: sensors and pictures of THIS tile ====================
