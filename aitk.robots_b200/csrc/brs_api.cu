@@ -53,6 +53,7 @@ struct brs_engine {
   uint32_t* d_rowgnd = nullptr;
   int flat_rows = 1;
   unsigned int* d_sched = nullptr;
+  unsigned long long* d_phase = nullptr;  // BRS_PHASE_TIMING builds
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
@@ -381,6 +382,9 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       return fail(BRS_ERR_CUDA, std::string("brs_create: scheduler allocation failed: ") + cudaGetErrorString(ce));
     }
   }
+#ifdef BRS_PHASE_TIMING
+  if (cudaMalloc((void**)&e->d_phase, 128) == cudaSuccess) cudaMemset(e->d_phase, 0, 128);
+#endif
   const int ncols = cfg->n_camera * e->cam_w;
   e->NR = env_int("BRS_NR", ncols >= 64 ? 2 : 1);
   if (e->NR != 1 && e->NR != 2 && e->NR != 4) e->NR = 1;
@@ -486,6 +490,23 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
 extern "C" int brs_destroy(brs_engine* e) {
   if (!e) return BRS_OK;
   cudaSetDevice(e->cfg.device);
+#ifdef BRS_PHASE_TIMING
+  if (e->d_phase) {
+    unsigned long long h[16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, e->d_phase, 128, cudaMemcpyDeviceToHost);
+    const char* nm[16] = {"w:end-barrier-wait", "w:table", "w:sense", "w:paint", "", "", "", "",
+                          "h:prep", "h:cull", "h:queue", "h:pairs", "h:commit", "h:direct", "h:idle", ""};
+    double tw = 0, th = 0;
+    for (int k = 0; k < 8; ++k) { tw += (double)h[k]; th += (double)h[8 + k]; }
+    fprintf(stderr, "[brs phase] workers:");
+    for (int k = 0; k < 8; ++k) if (h[k]) fprintf(stderr, " %s=%.1f%%", nm[k] + 2, 100.0 * h[k] / tw);
+    fprintf(stderr, "\n[brs phase] helper :");
+    for (int k = 8; k < 16; ++k) if (h[k]) fprintf(stderr, " %s=%.1f%%", nm[k] + 2, 100.0 * h[k] / th);
+    fprintf(stderr, "\n");
+    cudaFree(e->d_phase);
+  }
+#endif
   for (int b = 0; b < BRS_BUF_COUNT_; ++b)
     if (e->buf[b]) cudaFree(e->buf[b]);
   cudaFree(e->d_robots);
@@ -600,6 +621,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.groups = e->d_groups; p.gr_idx = e->d_gr_idx; p.dr_idx = e->d_dr_idx;
   p.cam_cs = e->d_camcs; p.row_sky = e->d_rowsky; p.row_gnd = e->d_rowgnd;
   p.sched = e->d_sched;
+  p.phase = e->d_phase;
   {
     void* args[] = {(void*)&p};
     CK(cudaLaunchKernel(e->kfn, dim3(e->grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));

@@ -155,6 +155,7 @@ struct KParams {
   const uint32_t* row_sky;  // [cam_h] rgba per image row
   const uint32_t* row_gnd;  // [cam_h]
   unsigned int* sched;      // [2] next tile, finished CTAs (self-resetting)
+  unsigned long long* phase;  // [16] cycle sums per phase (builds with -DBRS_PHASE_TIMING), else unused
 };
 
 // per-column paint record
@@ -219,6 +220,23 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
 #ifdef __CUDACC__
 
 #define BRS_PI_OVER_2 1.5707963267948966
+
+// Optional phase timing (nvcc -DBRS_PHASE_TIMING): thread 0 of the workers and thread 0 of
+// the helper team add the clock64() cycles of each phase to KParams::phase; brs_destroy
+// prints the shares.  This is how the helper team was found to be the critical path.
+// Note: BAR.SYNC does not block at issue, so a barrier wait shows up in the NEXT phase.
+#ifdef BRS_PHASE_TIMING
+#define BRS_PH_DECL long long ph_t0 = clock64()
+#define BRS_PH(cond, k)                                                         \
+  do {                                                                          \
+    const long long ph_t1 = clock64();                                          \
+    if (cond) atomicAdd(&p.phase[k], (unsigned long long)(ph_t1 - ph_t0));      \
+    ph_t0 = ph_t1;                                                              \
+  } while (0)
+#else
+#define BRS_PH_DECL
+#define BRS_PH(cond, k)
+#endif
 
 // inlining policy of the heavy FP64 helpers (code size vs call overhead), tunable at build time
 #ifndef BRS_INL_REFINE
@@ -847,9 +865,11 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
                                                 int* __restrict__ cq, float4* __restrict__ cpar, uint32_t bar,
                                                 uint32_t parity, bool staged) {
   const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
+  BRS_PH_DECL;
   if (ht == 0) cq[0] = 0;  // candidate queue of the collision phase
   prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, cpar, bar, parity, staged);
   team_sync(2, nth);
+  BRS_PH(ht == 0, 8);
   if (do_move) {
     // ---------------- COLLIDE ------------------------------------------------------
     // walls: GS threads per (world, robot) stride over its segments.  FP32 disc cull
@@ -860,13 +880,15 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
       // that four independent dependency chains are in flight (the helper team is latency
       // bound); what falls inside a disc goes to a queue
       {
-        const int total = nw * R * SC;
-        for (int base = ht; base < total; base += 4 * nth) {
+        const int total = nw * R * SC, lane = ht & 31;
+        // warp-uniform trip count: the queue pushes below are warp-aggregated (one shared-memory
+        // atomic per warp and step instead of one per candidate)
+        for (int b0 = ht - lane; b0 < total; b0 += 4 * nth) {
           int it_i[4], it_j[4];
           bool inside[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int item = base + k * nth;
+            const int item = b0 + lane + k * nth;
             const bool valid = item < total;
             const int i = valid ? (int)fdiv(item, p.dSC) : 0, j = valid ? item - i * SC : 0;
             const int wl = (int)fdiv(i, p.dR);
@@ -883,9 +905,14 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            const unsigned bal = __ballot_sync(0xffffffffu, inside[k]);
+            if (bal == 0u) continue;
+            int posb = 0;
+            if (lane == 0) posb = atomicAdd(&cq[0], __popc(bal));
+            posb = __shfl_sync(0xffffffffu, posb, 0);
             if (inside[k]) {
               const int i = it_i[k], j = it_j[k];
-              const int pos = atomicAdd(&cq[0], 1);
+              const int pos = posb + __popc(bal & ((1u << lane) - 1u));
               if (pos < BRS_CQ_MAX) {
                 cq[4 + pos] = (i << 16) | j;
               } else {  // queue full: test in place
@@ -897,6 +924,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
         }
       }
       team_sync(2, nth);
+      BRS_PH(ht == 0, 9);
       // pass 2: the queued (robot, wall) pairs, one per thread: FP32 edge classifier, then the
       // exact FP64 test for what is not a certain miss
       {
@@ -907,6 +935,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
           if (box_hits_wall(p, wsb, rawb, segtab + (size_t)wl * nvis, i, j, wl, r, SC)) cflag[i].x = 1;
         }
       }
+    BRS_PH(ht == 0, 10);
     // robots: proposal i against the committed box of o (pair_old) and, for o < i,
     // against the proposal of o (pair_new): Robot.step's list order becomes masks
       if (R > 1) {
@@ -938,6 +967,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
         }
       }
     team_sync(2, nth);
+    BRS_PH(ht == 0, 11);
   }
   // ---------------- COMMIT ---------------------------------------------------------
   // thread per (world, robot): replay the list order on the masks, commit or stall,
@@ -1008,12 +1038,14 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
         }
       }
     }
+  BRS_PH(ht == 0, 12);
   // camera worlds with a few extra sensors: the helper team has time to spare, the workers
   // do not -- run the direct-path sensors of this tile here, on the poses just committed
   if (do_sense && p.direct_on_helper) {
     team_sync(2, nth);
     sense_direct(p, ht, nth, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta);
   }
+  BRS_PH(ht == 0, 13);
 }
 
 template <int NR, bool BIG>
@@ -1063,6 +1095,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
   const int p_q = tid % pQc, p_rest = tid / pQc, p_RS = p.paint_rs;
   const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQc) / p_RS;
 
+  BRS_PH_DECL;
   // iteration -1 only lets the helper team step the CTA's first tile
   int tile = 0;
   for (int it = -1;; ++it) {
@@ -1106,6 +1139,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
       // every thread observes the phase of this tile's wall store itself before reading it
       if (!BIG) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+      BRS_PH(tid == 0, 0);  // = the wait at the end-of-tile barrier (see the note at BRS_PH)
 
       // ---------------- TABLE ------------------------------------------------------------
       // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,
@@ -1190,6 +1224,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         team_sync(1, NW);
       }
 
+      BRS_PH(tid == 0, 1);
       // ---------------- SENSE --------------------------------------------------------------
       // 5a. group path: camera column blocks, then grouped range sensors
       {
@@ -1277,6 +1312,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       // 5b. direct path (unless the helper team already ran it for this tile)
       if (do_sense && !p.direct_on_helper) sense_direct(p, tid, NW, lane, w0, nw, rawb, segtab, wsb, meta);
 
+      BRS_PH(tid == 0, 2);
       // ---------------- PAINT ----------------------------------------------------------------
       if (do_cam) {
         team_sync(1, NW);
@@ -1293,6 +1329,8 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       }
       }
     }
+    BRS_PH(tid == 0, 3);
+    BRS_PH(tid == NW, 14);
     __syncthreads();  // the teams meet: this tile is done, the next one is stepped
     tile = sched[1 + (buf ^ 1)];
     if (tile >= p.n_tiles) break;
