@@ -411,6 +411,13 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         hbm = {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes}
+        try:
+            # context: what a plain streaming-store kernel reaches on this GPU (the path is write-only)
+            wc = rb.measure_write_bw(local_rank, 512 << 20, 0, 5)
+            hbm["write_only_ceiling_gbs"] = wc
+            hbm["frac_of_write_only_ceiling"] = achieved / wc
+        except Exception:
+            pass
         fp32 = {"achieved": fp32_tflops, "peak": ffma_tflops or NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
                 "frac": fp32_tflops / (ffma_tflops or NOMINAL_FP32_TFLOPS),
                 "peak_source": "measured on this GPU (brs_measure_fp32_peak, dependent FFMA chains)" if ffma_tflops
