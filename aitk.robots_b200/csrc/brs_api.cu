@@ -495,8 +495,8 @@ extern "C" int brs_destroy(brs_engine* e) {
     unsigned long long h[16];
     cudaDeviceSynchronize();
     cudaMemcpy(h, e->d_phase, 128, cudaMemcpyDeviceToHost);
-    const char* nm[16] = {"w:end-barrier-wait", "w:table", "w:sense", "w:paint", "", "", "", "",
-                          "h:prep", "h:cull", "h:queue", "h:pairs", "h:commit", "h:direct", "h:idle", ""};
+    const char* nm[16] = {"w:tma-wait", "w:table", "w:sense", "w:paint", "w:WAIT-FOR-HELPER", "", "", "",
+                          "h:prep", "h:cull", "h:queue", "h:pairs", "h:commit", "h:direct", "h:-", "h:WAIT-FOR-WORKERS"};
     double tw = 0, th = 0;
     for (int k = 0; k < 8; ++k) { tw += (double)h[k]; th += (double)h[8 + k]; }
     fprintf(stderr, "[brs phase] workers:");

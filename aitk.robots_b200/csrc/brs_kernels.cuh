@@ -970,10 +970,86 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
     BRS_PH(ht == 0, 11);
   }
   // ---------------- COMMIT ---------------------------------------------------------
-  // thread per (world, robot): replay the list order on the masks, commit or stall,
-  // then publish everything that hangs off the final pose: the box as FP32 search
-  // segments and the origins / cones of the robot's ray groups.  (During this phase
-  // nobody reads DBOX / POSE / RCS of another robot: the replay only reads the masks.)
+  // 8 lanes per (world, robot), all of which replay the list order on the masks (a few
+  // bit operations), then split the rest: lane 0 commits or stalls (global pose / velocity
+  // / stalled, shared POSE / RCS), lanes 1-4 move one box corner each and publish one box
+  // edge as an FP32 search segment, lanes 5-7 publish the origins / cones of the robot's
+  // ray groups.  Every lane reads the state it needs (old or proposed, by the decision)
+  // before any lane writes: the phase is a short chain instead of a long serial one.
+  // (Nobody reads DBOX / POSE / RCS of ANOTHER robot here: the replay only reads the masks.)
+  // Tiles with many robots (more than two such passes) use one thread per robot instead.
+  if (nw * R * 8 <= 2 * nth) {
+    const int sub = ht & 7, nrob = nth >> 3;
+    for (int i0 = 0; i0 < nw * R; i0 += nrob) {  // warp-uniform trip count (__syncwarp below)
+      const int i = i0 + (ht >> 3);
+      const bool live = i < nw * R;
+      const int wl = live ? (int)fdiv(i, p.dR) : 0, r = live ? i - wl * R : 0, w = w0 + wl;
+      double* wsr = wsb + (size_t)(live ? i : 0) * BRS_WS_STRIDE;
+      const double* pr = wsr + BRS_WS_PROP;
+      bool hit = true;  // !do_move: keep the committed state
+      if (do_move && live) {
+        unsigned stalled_mask = 0;
+        for (int q = 0; q <= r; ++q) {
+          const int4 f = cflag[wl * R + q];
+          // robots before q: their proposal if they moved, their old box if they stalled;
+          // robots after q have not moved yet
+          const unsigned before = (1u << q) - 1u;
+          const unsigned m = ((unsigned)f.z & before & ~stalled_mask) | ((unsigned)f.y & (~before | stalled_mask));
+          hit = f.x || m;
+          if (hit) stalled_mask |= 1u << q;
+        }
+      }
+      // ---- reads (final state = proposal if the robot moves, committed state otherwise)
+      const int e = (sub - 1) & 3, e2 = (e + 1) & 3;
+      const double* fbox = hit ? wsr + BRS_WS_DBOX : pr;
+      const double bx1 = fbox[2 * e], by1 = fbox[2 * e + 1], bx2 = fbox[2 * e2], by2 = fbox[2 * e2 + 1];
+      const double fx = hit ? wsr[BRS_WS_POSE] : pr[8], fy = hit ? wsr[BRS_WS_POSE + 1] : pr[9];
+      const double fa = hit ? wsr[BRS_WS_POSE + 2] : pr[10];
+      const double fc = hit ? wsr[BRS_WS_RCS] : pr[14], fs = hit ? wsr[BRS_WS_RCS + 1] : pr[15];
+      const double pv0 = pr[11], pv1 = pr[12], pv2 = pr[13];
+      const int S = meta[wl].x;
+      __syncwarp();
+      // ---- writes
+      if (live && sub == 0 && do_move) {
+        const size_t o = ((size_t)w * R + r) * 3;
+        if (!hit) {
+          p.pose[o] = fx; p.pose[o + 1] = fy; p.pose[o + 2] = fa;
+          p.vel[o] = pv0; p.vel[o + 1] = pv1; p.vel[o + 2] = pv2;
+          wsr[BRS_WS_POSE] = fx; wsr[BRS_WS_POSE + 1] = fy; wsr[BRS_WS_POSE + 2] = fa;
+          wsr[BRS_WS_RCS] = fc; wsr[BRS_WS_RCS + 1] = fs;
+        } else {
+          p.vel[o] = 0.0; p.vel[o + 1] = 0.0; p.vel[o + 2] = 0.0;
+        }
+        p.stalled[(size_t)w * R + r] = (uint8_t)(hit ? 1 : 0);
+      } else if (live && sub >= 1 && sub <= 4) {
+        if (do_move && !hit) { wsr[BRS_WS_DBOX + 2 * e] = bx1; wsr[BRS_WS_DBOX + 2 * e + 1] = by1; }
+        if (do_rays) {
+          const float x1 = (float)bx1, y1 = (float)by1;
+          segtab[(size_t)wl * nvis + S + 4 * r + e] = make_float4(x1, y1, (float)bx2 - x1, (float)by2 - y1);
+        }
+      } else if (live && sub >= 5 && do_rays) {
+        for (int g = sub - 5; g < NG; g += 3) {
+          const GroupDev& gd = p.groups[g];
+          if (gd.robot != r) continue;
+          // mount point: robot centre + R(heading) * (mount offset in the a=0 frame)
+          const double x1 = da(fx, ds(dm(fc, gd.mx), dm(fs, gd.my)));
+          const double y1 = da(fy, da(dm(fs, gd.mx), dm(fc, gd.my)));
+          org[wl * NG + g] = make_double2(x1, y1);
+          const float cf = (float)fc, sf = (float)fs;
+          GroupCull gc;
+          gc.lo_x = cf * gd.lo_c - sf * gd.lo_s; gc.lo_y = sf * gd.lo_c + cf * gd.lo_s;
+          gc.hi_x = cf * gd.hi_c - sf * gd.hi_s; gc.hi_y = sf * gd.hi_c + cf * gd.hi_s;
+          gc.ax_x = cf * gd.ax_c - sf * gd.ax_s; gc.ax_y = sf * gd.ax_c + cf * gd.ax_s;
+          gc.range2 = gd.range * gd.range;
+          gc.has_cone = gd.has_cone;
+          gc.ox = (float)x1;
+          gc.oy = (float)y1;
+          gc._pad[0] = gc._pad[1] = 0.f;
+          gcull[wl * NG + g] = gc;
+        }
+      }
+    }
+  } else {
     for (int i = ht; i < nw * R; i += nth) {
       const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
       double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
@@ -1038,6 +1114,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
         }
       }
     }
+  }
   BRS_PH(ht == 0, 12);
   // camera worlds with a few extra sensors: the helper team has time to spare, the workers
   // do not -- run the direct-path sensors of this tile here, on the poses just committed
@@ -1139,7 +1216,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
       // every thread observes the phase of this tile's wall store itself before reading it
       if (!BIG) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
-      BRS_PH(tid == 0, 0);  // = the wait at the end-of-tile barrier (see the note at BRS_PH)
+      BRS_PH(tid == 0, 0);
 
       // ---------------- TABLE ------------------------------------------------------------
       // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,
@@ -1334,6 +1411,8 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
     __syncthreads();  // the teams meet: this tile is done, the next one is stepped
     tile = sched[1 + (buf ^ 1)];
     if (tile >= p.n_tiles) break;
+    BRS_PH(tid == 0, 4);    // (the load of `tile` is the first consumer of the barrier: its wait lands here)
+    BRS_PH(tid == NW, 15);
   }
 
   // self-resetting scheduler: the last CTA to leave zeroes both counters for the next launch
