@@ -125,7 +125,7 @@ struct KParams {
   int fused_table;   // TABLE phase: one warp per (world, group) builds and compacts in one pass
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
-  int NH;            // helper warps: prepare the next tile during the SENSE phase
+  int NH;            // helper warps: Robot.step of the next tile while the workers sense and paint this one
   FastDiv dR, dSC, dSQ, dTab, dNvis, dPair, dGT, dDT, dLT, dST, dCpb, dNG;
   unsigned flags;
   double dt, smell_cell, light_mult;
