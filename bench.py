@@ -232,7 +232,7 @@ def run_reference(args):
         "impl": "reference", "metric": "world-steps/sec", "value": v, "unit": "world-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
         # a "step" of this arm is a bounded sample; ms_per_step extrapolates it to the full batch
-        "ms_per_step": 1e3 * args.worlds / v, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * args.worlds * max(args.gpus, 1) / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "ray_segment_tests_per_sec": sum(tests) / len(tests),
         "cpu_baseline": {"value": v, "unit": "world-steps/s", "cores": cores, "kind": kind, "sample": sample},
