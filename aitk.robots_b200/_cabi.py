@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbrs.so")
 if os.environ.get("BRS_LIB"):  # tuning builds: another libbrs.so of the same ABI
     LIB_PATH = os.path.abspath(os.environ["BRS_LIB"])
 
-BRS_ABI_VERSION = 2
+BRS_ABI_VERSION = 3
 BRS_MAX_ROBOTS = 8
 
 # brs_buffer
@@ -132,6 +132,7 @@ SYMBOLS = [
     ("brs_count_tests", C.c_int, [_P, C.c_uint, _P, C.POINTER(C.c_ulonglong)]),
     ("brs_launch_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("brs_tile_info", C.c_int, [_P] + [C.POINTER(C.c_int)] * 5),
+    ("brs_path_info", C.c_int, [_P] + [C.POINTER(C.c_int)] * 2),
     ("brs_measure_write_bw", C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("brs_measure_fp32_peak", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]

@@ -6,6 +6,7 @@
 // entry point that produces results launches brs_step_kernel.
 #include "../../include/brs.h"
 #include "brs_kernels.cuh"
+#include "brs_wide.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -59,7 +60,14 @@ struct brs_engine {
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
   int gtasks = 0, dtasks = 0;
   bool big = false, direct_on_helper = false;
+  int fused_table = 0;
   const void* kfn = nullptr;
+  // the wide path (brs_wide.cuh): prep kernel + one-team-per-tile step kernel
+  bool wide = false;
+  double* d_ws = nullptr;  // [B][R][BRS_WS_STRIDE] robot records between the two kernels
+  int wNT = 32, wTW = 1, wSLG = 1, wSLD = 1, wSLL = 1, w_paint_rs = 1, w_tiles = 1, w_grid = 1, w_smem = 0, w_fused_table = 1;
+  bool w_big = false, pdl = true;
+  const void* w_kfn = nullptr;
 };
 
 static int pow2floor(int x) {
@@ -110,6 +118,10 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   if (cfg->seg_cap < 4 || cfg->seg_cap % 4) return fail(BRS_ERR_INVALID, "brs_create: seg_cap must be a positive multiple of 4");
   if (cfg->n_range < 0 || cfg->n_camera < 0 || cfg->n_light < 0 || cfg->n_smell < 0 || cfg->n_bulbs < 0)
     return fail(BRS_ERR_INVALID, "brs_create: negative device count");
+  if (cfg->grid_w < 0 || cfg->grid_h < 0 || ((cfg->grid_w > 0) != (cfg->grid_h > 0)))
+    return fail(BRS_ERR_INVALID, "brs_create: smell grid must be grid_w x grid_h > 0, or 0 x 0 for none");
+  if (cfg->grid_w > 0 && cfg->n_smell > 0 && !(cfg->smell_cell_size > 0))
+    return fail(BRS_ERR_INVALID, "brs_create: smell_cell_size must be > 0 when a smell grid exists");
   if (!cfg->robots) return fail(BRS_ERR_INVALID, "brs_create: robots == NULL");
   if ((cfg->n_range && !cfg->ranges) || (cfg->n_camera && !cfg->cameras) || (cfg->n_light && !cfg->lights) ||
       (cfg->n_smell && !cfg->smells))
@@ -155,7 +167,13 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   if (cfg->n_light && !cfg->n_bulbs) { /* lights without bulbs read 0: allowed */ }
 
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  {
+    cudaError_t ce = cudaGetDeviceProperties(&prop, cfg->device);
+    if (ce != cudaSuccess) {
+      delete e;
+      return fail(BRS_ERR_CUDA, std::string("brs_create: cudaGetDeviceProperties: ") + cudaGetErrorString(ce));
+    }
+  }
   e->sm_count = prop.multiProcessorCount;
 
   // ---- device descriptors, float64, same libm as the float64 reference -------
@@ -483,6 +501,100 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   }
   nb = std::min(nb, env_int("BRS_MAX_CTAS_PER_SM", 32));
   e->grid = std::max(1, std::min(e->n_tiles, nb * e->sm_count));
+  e->fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
+
+  // ---- the wide path: launch geometry ------------------------------------------
+  // One team (CTA) per tile, no helper warps.  A one-warp team wherever a tile of worlds fits
+  // ~1/20 of the SM's shared memory: 20+ independent warps per SM, synchronised with
+  // __syncwarp only.  Worlds too large for that get fewer, wider teams (so that the SM still
+  // holds ~20 warps) and, beyond half the SM's shared memory, read their walls from L2 / HBM.
+  {
+    // (one-warp teams read the camera tables through L1: see make_wide_layout)
+    auto wsmem_nt = [&](int tw, bool big, int nt_) {
+      return make_wide_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h, !big, nt_ > 32).total;
+    };
+    auto wsmem = [&](int tw, bool big) { return wsmem_nt(tw, big, 32); };
+    const int target_warps = env_int("BRS_WWARPS", 20);
+    int nt = 32, wtw = 1;
+    bool wbig = false;
+    if (wsmem(1, false) <= smem_sm / 16) {
+      // worlds per tile: fill the warp's lanes with ray tasks, within the budget, keeping >= 4
+      // tiles per resident team for the dynamic scheduler
+      const int wbudget = std::max(smem_sm / target_warps, wsmem(1, false));
+      const int cap_tiles = std::max(1, cfg->n_worlds / (e->sm_count * target_warps * 4));
+      int tw_max = std::min(32, cap_tiles);
+      while (tw_max > 1 && wsmem(tw_max, false) > wbudget) --tw_max;
+      double best = -1;
+      for (int t = 1; t <= tw_max; ++t) {
+        const int n = t * tasks, passes = (n + 31) / 32;
+        const double eff = (double)n / (passes * 32.0);
+        if (eff > best + 0.04) { best = eff; wtw = t; }
+      }
+    } else {
+      wbig = wsmem(1, false) > smem_sm / 2;
+      const int per_sm = std::max(1, smem_sm / std::max(wsmem_nt(1, wbig, 64), 1));
+      nt = 32 * std::min(8, pow2ceil((target_warps + per_sm - 1) / per_sm));
+    }
+    wbig = env_int("BRS_WBIG", wbig ? 1 : 0) != 0;
+    nt = env_int("BRS_WNT", nt);
+    nt = std::max(32, std::min(256, nt / 32 * 32));
+    wtw = env_int("BRS_WTW", wtw);
+    wtw = std::max(1, std::min(wtw, cfg->n_worlds));
+    while (wtw > 1 && (size_t)wsmem_nt(wtw, wbig, nt) > prop.sharedMemPerBlockOptin) --wtw;
+    e->wNT = nt; e->wTW = wtw; e->w_big = wbig;
+    e->w_smem = wsmem_nt(wtw, wbig, nt);
+    e->w_tiles = (cfg->n_worlds + wtw - 1) / wtw;
+    e->wSLG = gtasks ? std::min(32, pow2floor(std::max(nt / (gtasks * wtw), 1))) : 1;
+    e->wSLD = e->n_dr ? std::min(32, pow2floor(std::max(nt / (e->n_dr * wtw), 1))) : 1;
+    e->wSLL = cfg->n_light ? std::min(32, pow2floor(std::max(nt / (cfg->n_light * wtw), 1))) : 1;
+    {
+      const int Q = std::max(e->cam_w / 4, 1);
+      const int slots = std::max(nt / std::min(Q, nt), 1);
+      const int nislot = std::max(1, std::min(wtw * std::max(cfg->n_camera, 1), slots));
+      e->w_paint_rs = std::max(1, slots / nislot);
+    }
+    e->w_fused_table = env_int("BRS_FUSED_TABLE", wtw * e->n_group >= nt / 32 ? 1 : 0);
+    const bool nr2 = e->NR == 2;
+    const void* wk;
+    // register caps by team size: ~20 warps per SM for teams of 1, 2 and 4 warps, 16 for 8
+#define BRS_WK(BIGF, NTM, CT) (nr2 ? (const void*)brs_wide_kernel<2, BIGF, NTM, CT> : (const void*)brs_wide_kernel<1, BIGF, NTM, CT>)
+    if (wbig)
+      wk = BRS_WK(true, 256, 2);
+    else if (nt <= 32)
+      wk = BRS_WK(false, 32, BRS_WIDE_WARP_CTAS);
+    else if (nt <= 64)
+      wk = BRS_WK(false, 64, 10);
+    else if (nt <= 128)
+      wk = BRS_WK(false, 128, 5);
+    else
+      wk = BRS_WK(false, 256, 2);
+#undef BRS_WK
+    e->w_kfn = wk;
+    bool wide_ok = (size_t)e->w_smem <= prop.sharedMemPerBlockOptin;
+    int wnb = 0;
+    if (wide_ok) {
+      ce = cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, e->w_smem);
+      if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wnb, wk, nt, e->w_smem);
+      wide_ok = ce == cudaSuccess && wnb >= 1;
+      if (!wide_ok) cudaGetLastError();
+    }
+    e->w_grid = std::max(1, std::min(e->w_tiles, std::max(wnb, 1) * e->sm_count));
+    // which path: the fused kernel overlaps Robot.step with the rays inside a CTA, which pays
+    // when a launch has few tiles per CTA (config 2: 4096 picture-bound worlds); the wide path
+    // needs enough worlds to fill every SM with independent teams several times over
+    const bool auto_wide = cfg->n_worlds >= env_int("BRS_WIDE_MIN_WORLDS", 16384);
+    e->wide = wide_ok && env_int("BRS_WIDE", auto_wide ? 1 : 0) != 0;
+    e->pdl = env_int("BRS_PDL", 1) != 0;
+    if (wide_ok) {
+      const size_t bytes = (size_t)cfg->n_worlds * R * BRS_WS_STRIDE * 8 + 64;
+      ce = cudaMalloc((void**)&e->d_ws, bytes);
+      if (ce == cudaSuccess) ce = cudaMemset(e->d_ws, 0, bytes);
+      if (ce != cudaSuccess) {
+        brs_destroy(e);
+        return fail(BRS_ERR_CUDA, std::string("brs_create: robot record allocation failed: ") + cudaGetErrorString(ce));
+      }
+    }
+  }
   *out = e;
   return BRS_OK;
 }
@@ -521,6 +633,7 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_camcs);
   cudaFree(e->d_rowsky);
   cudaFree(e->d_rowgnd);
+  cudaFree(e->d_ws);
   delete e;
   return BRS_OK;
 }
@@ -571,23 +684,31 @@ extern "C" int brs_download(brs_engine* e, int which, void* host, int first_worl
   return BRS_OK;
 }
 
-extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
-  if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
-  if (!(flags & BRS_STEP_ALL)) return BRS_OK;
-  CK(cudaSetDevice(e->cfg.device));
+// Kernel parameters of one step: everything but flags, dt and the (rebindable) output
+// pointers is fixed at brs_create.
+static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide) {
   const brs_config& c = e->cfg;
-  KParams p;
   memset(&p, 0, sizeof(p));
   p.n_worlds = c.n_worlds; p.n_robots = c.n_robots; p.seg_cap = c.seg_cap; p.n_bulbs = c.n_bulbs;
   p.grid_w = c.grid_w; p.grid_h = c.grid_h;
   p.n_range = c.n_range; p.n_camera = c.n_camera; p.n_light = c.n_light; p.n_smell = c.n_smell;
   p.cam_w = e->cam_w; p.cam_h = e->cam_h;
   p.n_group = e->n_group; p.n_gr = e->n_gr; p.n_dr = e->n_dr;
-  p.TW = e->TW; p.n_tiles = e->n_tiles; p.GS = e->GS; p.SLG = e->SLG; p.SLD = e->SLD; p.SLL = e->SLL; p.paint_rs = e->paint_rs;
+  p.GS = e->GS;
   p.flat_rows = e->flat_rows;
-  p.direct_on_helper = e->direct_on_helper ? 1 : 0;
-  p.fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
-  p.NW = e->NW; p.NH = e->NH;
+  if (wide) {
+    p.TW = e->wTW; p.n_tiles = e->w_tiles; p.SLG = e->wSLG; p.SLD = e->wSLD; p.SLL = e->wSLL; p.paint_rs = e->w_paint_rs;
+    p.direct_on_helper = 0;
+    p.fused_table = e->w_fused_table;
+    p.NW = e->wNT; p.NH = 0;
+    p.cq_max = wide_cq_max(e->wTW, c.n_robots);
+  } else {
+    p.TW = e->TW; p.n_tiles = e->n_tiles; p.SLG = e->SLG; p.SLD = e->SLD; p.SLL = e->SLL; p.paint_rs = e->paint_rs;
+    p.direct_on_helper = e->direct_on_helper ? 1 : 0;
+    p.fused_table = e->fused_table;
+    p.NW = e->NW; p.NH = e->NH;
+    p.cq_max = BRS_CQ_MAX;
+  }
   {
     const int R = c.n_robots, nvis = c.seg_cap + 4 * R;
     p.dR = make_fastdiv(R); p.dSC = make_fastdiv(c.seg_cap); p.dSQ = make_fastdiv(c.seg_cap / 4); p.dTab = make_fastdiv(std::max(e->n_group * nvis, 1));
@@ -622,9 +743,35 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   p.cam_cs = e->d_camcs; p.row_sky = e->d_rowsky; p.row_gnd = e->d_rowgnd;
   p.sched = e->d_sched;
   p.phase = e->d_phase;
-  {
-    void* args[] = {(void*)&p};
+  p.wsg = e->d_ws;
+}
+
+extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
+  if (!(flags & BRS_STEP_ALL)) return BRS_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  KParams p;
+  fill_params(e, p, time_step, flags, e->wide);
+  void* args[] = {(void*)&p};
+  if (!e->wide) {
     CK(cudaLaunchKernel(e->kfn, dim3(e->grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
+  } else {
+    // prep (thread per robot half), then the step kernel under programmatic dependent launch:
+    // its prologue and first wall copies overlap the prep kernel, griddepcontrol.wait orders the rest
+    const unsigned halves = (unsigned)e->cfg.n_worlds * e->cfg.n_robots * ((flags & BRS_STEP_MOVE) ? 2u : 1u);
+    CK(cudaLaunchKernel((const void*)brs_prep_kernel, dim3((halves + 255u) / 256u), dim3(256), args, 0, (cudaStream_t)stream));
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(e->w_grid);
+    lc.blockDim = dim3(e->wNT);
+    lc.dynamicSmemBytes = (size_t)e->w_smem;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    CK(cudaLaunchKernelExC(&lc, e->w_kfn, args));
   }
   CK(cudaGetLastError());
   return BRS_OK;
@@ -676,19 +823,26 @@ extern "C" int brs_count_tests(brs_engine* e, unsigned flags, void* stream, unsi
 
 extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem_bytes, int* sm_count) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_launch_info: null engine");
-  if (threads) *threads = e->T;
-  if (ctas) *ctas = e->grid;
-  if (smem_bytes) *smem_bytes = e->smem;
+  if (threads) *threads = e->wide ? e->wNT : e->T;
+  if (ctas) *ctas = e->wide ? e->w_grid : e->grid;
+  if (smem_bytes) *smem_bytes = e->wide ? e->w_smem : e->smem;
   if (sm_count) *sm_count = e->sm_count;
+  return BRS_OK;
+}
+
+extern "C" int brs_path_info(brs_engine* e, int* wide, int* launches_per_step) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_path_info: null engine");
+  if (wide) *wide = e->wide ? 1 : 0;
+  if (launches_per_step) *launches_per_step = e->wide ? 2 : 1;
   return BRS_OK;
 }
 
 extern "C" int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* workers, int* cols_per_thread,
                              int* n_groups) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_tile_info: null engine");
-  if (worlds_per_tile) *worlds_per_tile = e->TW;
-  if (n_tiles) *n_tiles = e->n_tiles;
-  if (workers) *workers = e->NW;
+  if (worlds_per_tile) *worlds_per_tile = e->wide ? e->wTW : e->TW;
+  if (n_tiles) *n_tiles = e->wide ? e->w_tiles : e->n_tiles;
+  if (workers) *workers = e->wide ? e->wNT : e->NW;
   if (cols_per_thread) *cols_per_thread = e->NR;
   if (n_groups) *n_groups = e->n_group;
   return BRS_OK;

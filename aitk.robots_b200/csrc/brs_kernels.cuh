@@ -55,6 +55,10 @@
 #define BRS_PAINT_UNROLL 4  // rows in flight per thread in the PAINT fast path
 #endif
 
+#ifndef BRS_PAINT_ZONES
+#define BRS_PAINT_ZONES 1  // constant-quad fast rows in PAINT (0: per-pixel compare / select on every row)
+#endif
+
 namespace brs {
 
 constexpr int kPaintUnroll = BRS_PAINT_UNROLL;
@@ -126,6 +130,7 @@ struct KParams {
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
   int NH;            // helper warps: Robot.step of the next tile while the workers sense and paint this one
+  int cq_max;        // capacity of the collision candidate queue (<= BRS_CQ_MAX; overflow is tested in place)
   FastDiv dR, dSC, dSQ, dTab, dNvis, dPair, dGT, dDT, dLT, dST, dCpb, dNG;
   unsigned flags;
   double dt, smell_cell, light_mult;
@@ -156,6 +161,7 @@ struct KParams {
   const uint32_t* row_gnd;  // [cam_h]
   unsigned int* sched;      // [2] next tile, finished CTAs (self-resetting)
   unsigned long long* phase;  // [16] cycle sums per phase (builds with -DBRS_PHASE_TIMING), else unused
+  double* wsg;              // [B][R][BRS_WS_STRIDE] robot records of the wide path (prep kernel -> step kernel)
 };
 
 // per-column paint record
@@ -171,14 +177,20 @@ struct __align__(16) Strip {
   float dist;
 };
 
-// per-(world, robot) working state in shared memory, doubles:
-//   pose[3] vel[3] rcs[2] dbox[8] prop[16] = 32
+// per-(world, robot) working state, doubles (shared memory; the wide path also keeps it in
+// HBM between its two kernels):
+//   pose[3] meta[1] cpar[2] rcs[2] dbox[8] prop[16] pad[2] = 34
+// cpar = float4 (proposed centre x, y, (circumradius + margin)^2, 0): the FP32 disc of the
+// collision cull.  The stride is 34 doubles = 17 x 16 bytes: records stay 16-byte aligned
+// (TMA bulk copies, the float4 at CPAR) and lane-per-robot accesses spread over the banks
+// (a stride of 32 doubles put every robot's field into the same bank).
 #define BRS_WS_POSE 0
-#define BRS_WS_VEL 3
+#define BRS_WS_META 3  // robot 0 of a world, wide path: int2 (segment count, bits of the world extent)
+#define BRS_WS_CPAR 4
 #define BRS_WS_RCS 6
 #define BRS_WS_DBOX 8
 #define BRS_WS_PROP 16
-#define BRS_WS_STRIDE 32
+#define BRS_WS_STRIDE 34
 // prop: [0..8) proposed box corners, [8..11) proposed pose, [11..14) proposed velocity, [14..16) cos/sin
 
 // shared memory carve-up, byte offsets; mirrored on the host for the launch size
@@ -209,7 +221,7 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   L.rowsky = o; o += cam_h * 4;
   L.rowgnd = o; o += cam_h * 4;
   o = align_up(o, 16);
-  L.cpar = o; o += TW * R * 16;  // collision disc per (world, robot): centre, radius^2 (helper-only, transient)
+  L.cpar = o;  // (the collision disc moved into the ws record, BRS_WS_CPAR)
   L.cq = o; o += 4 * 256;  // collision candidate queue: count + BRS_CQ_MAX packed (robot item, wall)
   L.mbar = o; o += 2 * 8;
   L.sched = o; o += 16;
@@ -258,6 +270,10 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
 #define BRS_SMALL_CTAS 4
 #define BRS_BIG_THREADS 288
 #define BRS_BIG_CTAS 2
+// one-warp teams of the wide path: resident CTAs per SM the register cap is set for
+#ifndef BRS_WIDE_WARP_CTAS
+#define BRS_WIDE_WARP_CTAS 20
+#endif
 
 // ---- exact (never contracted) float64 helpers --------------------------------
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
@@ -476,29 +492,76 @@ __device__ __forceinline__ void mount_point(const double* wsr, double mx, double
 
 // Paint rows r0, r0+rstep, ... of the 4 columns of quad q of one picture
 // (upstream Camera.take_picture: sky above, shaded wall, ground below, then the
-// strips of other robots back to front).  The common case -- flat sky and ground
-// colours, every column hit a wall, no robot in sight -- is a tight loop of two
-// compares and two selects per pixel; everything else takes the generic loop.
+// strips of other robots back to front).
+//
+// Fast path (flat sky and ground colours, every column hit a wall, no robot in sight).
+// `oct`: the 8 lanes of an aligned lane octet hold the 8 adjacent quads of one 128-byte
+// line of the same rows (picture width a multiple of 32).  They reduce the wall tops and
+// bottoms of their 32 columns with shuffles; rows above every wall top are one constant
+// quad (sky), rows inside every wall and rows below every wall bottom likewise, and are
+// written by tight store loops: ~5 issue slots per 16-byte store instead of the ~22 of
+// the per-pixel form (2 compares + 2 selects per pixel), which only the few rows where the
+// 32 columns disagree still take.  A line is always written by ONE store instruction.
+// Everything else (gradients, blank columns, robot strips) takes the generic loop.
+__device__ __forceinline__ uint4 quad_pixels(const ColInfo (&ci)[4], int j, uint32_t sky, uint32_t gnd) {
+  uint32_t px[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) px[k] = j < ci[k].top ? sky : (j < ci[k].bot ? ci[k].rgba : gnd);
+  return make_uint4(px[0], px[1], px[2], px[3]);
+}
 __device__ __forceinline__ void paint_rows(uint4* __restrict__ out, const ColInfo* __restrict__ cinf,
                                            const Strip* __restrict__ strips, int strips_per_col,
                                            const uint32_t* __restrict__ rowsky, const uint32_t* __restrict__ rowgnd,
-                                           bool flat, int q, int Q, int r0, int rstep, int H) {
+                                           bool flat, bool oct, int lane, int q, int Q, int r0, int rstep, int H) {
   ColInfo ci[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) ci[k] = cinf[4 * q + k];
-  const bool slow = ((ci[0].n_robot | ci[1].n_robot | ci[2].n_robot | ci[3].n_robot) != 0) ||
-                    ((ci[0].top | ci[1].top | ci[2].top | ci[3].top) < 0) || !flat;
+  bool slow = ((ci[0].n_robot | ci[1].n_robot | ci[2].n_robot | ci[3].n_robot) != 0) ||
+              ((ci[0].top | ci[1].top | ci[2].top | ci[3].top) < 0) || !flat;
   uint4* o = out + (size_t)r0 * Q + q;
   const size_t ostep = (size_t)rstep * Q;
+#if BRS_PAINT_ZONES
+  if (oct) {
+    const uint32_t gm = 0xFFu << (lane & 24);
+    slow = (__ballot_sync(gm, slow) & gm) != 0u;  // the octet takes one path together
+    if (!slow) {
+      const uint32_t sky = rowsky[0], gnd = rowgnd[0];
+      int t0 = min(min(ci[0].top, ci[1].top), min(ci[2].top, ci[3].top));
+      int t1 = max(max(ci[0].top, ci[1].top), max(ci[2].top, ci[3].top));
+      int b0 = min(min(ci[0].bot, ci[1].bot), min(ci[2].bot, ci[3].bot));
+      int b1 = max(max(ci[0].bot, ci[1].bot), max(ci[2].bot, ci[3].bot));
+#pragma unroll
+      for (int x = 1; x < 8; x <<= 1) {
+        t0 = min(t0, __shfl_xor_sync(gm, t0, x));
+        t1 = max(t1, __shfl_xor_sync(gm, t1, x));
+        b0 = min(b0, __shfl_xor_sync(gm, b0, x));
+        b1 = max(b1, __shfl_xor_sync(gm, b1, x));
+      }
+      b1 = max(b1, t1);
+      const uint4 skyq = make_uint4(sky, sky, sky, sky), gndq = make_uint4(gnd, gnd, gnd, gnd);
+      const uint4 wallq = make_uint4(ci[0].rgba, ci[1].rgba, ci[2].rgba, ci[3].rgba);
+      int j = r0;
+      const int e1 = min(t0, H), e2 = min(t1, H), e3 = min(b0, H), e4 = min(b1, H);
+      // (not unrolled: the compiler's remainder handling costs an integer division per loop,
+      //  which at 16-32 rows per thread is more than the unrolling saves)
+#pragma unroll 1
+      for (; j < e1; j += rstep, o += ostep) __stcs(o, skyq);
+#pragma unroll 1
+      for (; j < e2; j += rstep, o += ostep) __stcs(o, quad_pixels(ci, j, sky, gnd));
+#pragma unroll 1
+      for (; j < e3; j += rstep, o += ostep) __stcs(o, wallq);
+#pragma unroll 1
+      for (; j < e4; j += rstep, o += ostep) __stcs(o, quad_pixels(ci, j, sky, gnd));
+#pragma unroll 1
+      for (; j < H; j += rstep, o += ostep) __stcs(o, gndq);
+      return;
+    }
+  }
+#endif
   if (!slow) {
     const uint32_t sky = rowsky[0], gnd = rowgnd[0];
 #pragma unroll kPaintUnroll
-    for (int j = r0; j < H; j += rstep, o += ostep) {
-      uint32_t px[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) px[k] = j < ci[k].top ? sky : (j < ci[k].bot ? ci[k].rgba : gnd);
-      __stcs(o, make_uint4(px[0], px[1], px[2], px[3]));
-    }
+    for (int j = r0; j < H; j += rstep, o += ostep) __stcs(o, quad_pixels(ci, j, sky, gnd));
     return;
   }
 #pragma unroll 1
@@ -613,29 +676,35 @@ __device__ __forceinline__ void team_sync(int id, int nthreads) {
 // the 4 edges against the wall widened by an explicit error bound, then the exact float64
 // 4-edge test for what is not a certain miss.
 #define BRS_CQ_MAX 252
+// FP32 classification of ONE box edge (ax,ay)->(bx2,by2) of a proposal against wall s =
+// (x1, y1, ex, ey), widened by an explicit error bound: false = certain miss.
+__device__ __forceinline__ bool edge_maybe_hits(const KParams& p, const double* __restrict__ pr, int r, const float4 s,
+                                                double ax, double ay, double bx2, double by2) {
+  const float cx = (float)pr[8], cy = (float)pr[9];
+  const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
+  const float cscale = 4e-7f * (fabsf(cx) + fabsf(cy) + rad + 1.f);
+  const float pcx = (float)ax, pcy = (float)ay;
+  const float pex = (float)(bx2 - ax), pey = (float)(by2 - ay);
+  const float bx = pcx - s.x, by = pcy - s.y;  // edge start relative to the wall start
+  const float den = s.w * pex - s.z * pey;
+  const float na = s.z * by - s.w * bx, nb = pex * by - pey * bx;
+  // error bound: coordinates carry ~6e-8 * |coordinate| of FP32 rounding, which the
+  // cross products scale by the edge / wall lengths; products add ~1e-7 relative
+  const float ad = fabsf(den);
+  const float tol = cscale * (fabsf(s.z) + fabsf(s.w) + fabsf(pex) + fabsf(pey)) + 1e-5f * (fabsf(na) + fabsf(nb) + ad);
+  const float sa_ = den < 0.f ? -na : na, sb_ = den < 0.f ? -nb : nb;
+  return !(sa_ < -tol || sa_ > ad + tol || sb_ < -tol || sb_ > ad + tol);
+}
 __device__ __forceinline__ bool box_hits_wall(const KParams& p, const double* __restrict__ wsb,
                                               const uint32_t* __restrict__ rawb, const float4* __restrict__ st, int i,
                                               int j, int wl, int r, int SC) {
   const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
-  const float cx = (float)pr[8], cy = (float)pr[9];
-  const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
-  const float cscale = 4e-7f * (fabsf(cx) + fabsf(cy) + rad + 1.f);
   const float4 s = st[j];
   bool maybe = false;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int e2 = (e + 1) & 3;
-    const float pcx = (float)pr[2 * e], pcy = (float)pr[2 * e + 1];
-    const float pex = (float)(pr[2 * e2] - pr[2 * e]), pey = (float)(pr[2 * e2 + 1] - pr[2 * e + 1]);
-    const float bx = pcx - s.x, by = pcy - s.y;  // edge start relative to the wall start
-    const float den = s.w * pex - s.z * pey;
-    const float na = s.z * by - s.w * bx, nb = pex * by - pey * bx;
-    // error bound: coordinates carry ~6e-8 * |coordinate| of FP32 rounding, which the
-    // cross products scale by the edge / wall lengths; products add ~1e-7 relative
-    const float ad = fabsf(den);
-    const float tol = cscale * (fabsf(s.z) + fabsf(s.w) + fabsf(pex) + fabsf(pey)) + 1e-5f * (fabsf(na) + fabsf(nb) + ad);
-    const float sa_ = den < 0.f ? -na : na, sb_ = den < 0.f ? -nb : nb;
-    maybe |= !(sa_ < -tol || sa_ > ad + tol || sb_ < -tol || sb_ > ad + tol);
+    maybe |= edge_maybe_hits(p, pr, r, s, pr[2 * e], pr[2 * e + 1], pr[2 * e2], pr[2 * e2 + 1]);
   }
   if (!maybe) return false;
   const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
@@ -651,81 +720,74 @@ __device__ __forceinline__ bool box_hits_wall(const KParams& p, const double* __
   return hit;
 }
 
-// PREP of one tile, run by `nth` helper threads (index ht): robot state HBM ->
-// shared, heading trig, proposed pose and velocity, committed and proposed box
-// corners (compute_boundingbox), collision flags cleared, per-world meta and the
-// FP32 table of the static walls (start point and delta) from the TMA-landed store.
-__device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
-                                             const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
-                                             double* __restrict__ wsb, int4* __restrict__ cflag,
-                                             int2* __restrict__ meta, float4* __restrict__ cpar, uint32_t bar,
-                                             uint32_t parity, bool staged) {
-  const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
-  // per-world meta first: its global loads overlap the float64 chain below
+// PREP of one robot half -- the committed pose (heading trig, box corners) or the proposal
+// (velocity ramp, proposed pose, its trig and corners, the FP32 disc of the collision cull)
+// -- written branch-free around ONE sincos call, so that a robot is two independent
+// float64 chains on two lanes.  `wsr` is the robot's BRS_WS_STRIDE record (shared memory in
+// the fused kernel, HBM in the wide path's prep kernel).  Robot.step / compute_boundingbox
+// of the restatement (oracle/aitk_oracle.py Robot.step).
+__device__ __forceinline__ void prep_robot_half(const KParams& p, int w, int r, bool prop, double* __restrict__ wsr) {
+  const int R = p.n_robots;
+  const RobotDev& rd = p.robots[r];
+  const size_t o = ((size_t)w * R + r) * 3;
+  const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
+  const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
+  double vx = v0, vy = v1, va = v2, pa = a;
+  if (prop) {
+    const double* tv = p.tvel + o;
+    vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
+    vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
+    va = deltav(tv[2], v2, rd.va_ramp, p.dt);
+    pa = ds(a, dm(va, p.dt));
+  }
+  double sn, cs;
+  sincos(prop ? da(-pa, BRS_PI_OVER_2) : a, &sn, &cs);
+  // heading cos / sin of this half: (cos a, sin a), or (cos pa, sin pa) = (sin, cos)(pi/2 - pa)
+  const double c = prop ? sn : cs, sgn = prop ? cs : sn;
+  double px = x, py = y;
+  if (prop) {
+    // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
+    px = da(x, da(dm(vx, sn), dm(dm(vy, cs), p.dt)));
+    py = da(y, ds(dm(vx, cs), dm(dm(vy, sn), p.dt)));
+  }
+  double* box = wsr + (prop ? BRS_WS_PROP : BRS_WS_DBOX);
+  // corner = centre + R(heading) * (corner offset in the a=0 frame)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double ox = rd.cox[k], oy = rd.coy[k];
+    box[2 * k] = da(px, ds(dm(c, ox), dm(sgn, oy)));
+    box[2 * k + 1] = da(py, da(dm(sgn, ox), dm(c, oy)));
+  }
+  if (prop) {
+    double* pr = wsr + BRS_WS_PROP;
+    pr[8] = px; pr[9] = py; pr[10] = pa;
+    pr[11] = vx; pr[12] = vy; pr[13] = va;
+    pr[14] = c; pr[15] = sgn;
+    // FP32 disc of the cull: proposed centre, (circumradius + margin)^2
+    const float cxf = (float)px, cyf = (float)py;
+    const float rad = (float)rd.radius + p.cull_margin + 1e-5f * (fabsf(cxf) + fabsf(cyf));
+    *(float4*)(wsr + BRS_WS_CPAR) = make_float4(cxf, cyf, rad * rad, 0.f);
+  } else {
+    wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
+    wsr[BRS_WS_RCS] = c;
+    wsr[BRS_WS_RCS + 1] = sgn;
+  }
+}
+
+// Per-world meta (segment count, world extent) and the FP32 table of the static walls
+// (start point and delta) of one tile, by `nth` threads (index ht).  `rawb` is the tile's
+// wall store: TMA-landed shared memory (the caller has waited for it) or L2 / HBM.
+__device__ __forceinline__ void build_meta(const KParams& p, int w0, int nw, int ht, int nth, int2* __restrict__ meta) {
+  const int SC = p.seg_cap;
   for (int wl = ht; wl < nw; wl += nth) {
     const int w = w0 + wl;
     meta[wl].x = min(max(p.seg_count[w], 0), SC);
     meta[wl].y = __float_as_int(fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]));
   }
-  // Each robot is two independent halves on two lanes -- the committed pose (heading trig,
-  // box corners) and the proposal (velocity ramp, proposed pose, its trig and corners) --
-  // written branch-free around ONE sincos call, so the float64 dependency chain of PREP is
-  // half as long and twice as many lanes work.
-  const int nhalf = do_move ? 2 : 1;
-  for (int h = ht; h < nw * R * nhalf; h += nth) {
-    const int i = do_move ? (h >> 1) : h;
-    const bool prop = do_move && (h & 1);
-    const int wl = (int)fdiv(i, p.dR), r = i - wl * R, w = w0 + wl;
-    const RobotDev& rd = p.robots[r];
-    double* wsr = wsb + (size_t)i * BRS_WS_STRIDE;
-    const size_t o = ((size_t)w * R + r) * 3;
-    const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
-    const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
-    double vx = v0, vy = v1, va = v2, pa = a;
-    if (prop) {
-      const double* tv = p.tvel + o;
-      vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
-      vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
-      va = deltav(tv[2], v2, rd.va_ramp, p.dt);
-      pa = ds(a, dm(va, p.dt));
-    }
-    double sn, cs;
-    sincos(prop ? da(-pa, BRS_PI_OVER_2) : a, &sn, &cs);
-    // heading cos / sin of this half: (cos a, sin a), or (cos pa, sin pa) = (sin, cos)(pi/2 - pa)
-    const double c = prop ? sn : cs, sgn = prop ? cs : sn;
-    double px = x, py = y;
-    if (prop) {
-      // vx*sin + vy*cos*dt ; vx*cos - vy*sin*dt  (dt binds to the vy term)
-      px = da(x, da(dm(vx, sn), dm(dm(vy, cs), p.dt)));
-      py = da(y, ds(dm(vx, cs), dm(dm(vy, sn), p.dt)));
-    }
-    double* box = wsr + (prop ? BRS_WS_PROP : BRS_WS_DBOX);
-    // corner = centre + R(heading) * (corner offset in the a=0 frame)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double ox = rd.cox[k], oy = rd.coy[k];
-      box[2 * k] = da(px, ds(dm(c, ox), dm(sgn, oy)));
-      box[2 * k + 1] = da(py, da(dm(sgn, ox), dm(c, oy)));
-    }
-    if (prop) {
-      double* pr = wsr + BRS_WS_PROP;
-      pr[8] = px; pr[9] = py; pr[10] = pa;
-      pr[11] = vx; pr[12] = vy; pr[13] = va;
-      pr[14] = c; pr[15] = sgn;
-      // FP32 disc of the cull: proposed centre, (circumradius + margin)^2
-      const float cxf = (float)px, cyf = (float)py;
-      const float rad = (float)rd.radius + p.cull_margin + 1e-5f * (fabsf(cxf) + fabsf(cyf));
-      cpar[i] = make_float4(cxf, cyf, rad * rad, 0.f);
-    } else {
-      wsr[BRS_WS_POSE] = x; wsr[BRS_WS_POSE + 1] = y; wsr[BRS_WS_POSE + 2] = a;
-      wsr[BRS_WS_VEL] = v0; wsr[BRS_WS_VEL + 1] = v1; wsr[BRS_WS_VEL + 2] = v2;
-      wsr[BRS_WS_RCS] = c;
-      wsr[BRS_WS_RCS + 1] = sgn;
-      cflag[i] = make_int4(0, 0, 0, 0);
-    }
-  }
-  // the tile's wall store was requested before the robot state: by now it has usually landed
-  if (staged) mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void build_segtab(const KParams& p, int nw, int ht, int nth,
+                                             const uint32_t* __restrict__ rawb, float4* __restrict__ segtab) {
+  const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
   // four walls per thread and step: one 16-byte load per SoA row (x1|y1|x2|y2), so that four
   // independent loads are in flight -- the big shape reads them straight from L2 / HBM
   const int SQ = SC >> 2;
@@ -743,6 +805,29 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
       dst[k] = make_float4(ax, ay, __uint_as_float(x2[k]) - ax, __uint_as_float(y2[k]) - ay);
     }
   }
+}
+
+// PREP of one tile, run by `nth` helper threads (index ht) of the fused kernel: robot state
+// HBM -> shared (two lanes per robot), collision flags cleared, per-world meta and the
+// FP32 table of the static walls from the TMA-landed store.
+__device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
+                                             const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
+                                             double* __restrict__ wsb, int4* __restrict__ cflag,
+                                             int2* __restrict__ meta, uint32_t bar, uint32_t parity, bool staged) {
+  const int R = p.n_robots;
+  // per-world meta first: its global loads overlap the float64 chain below
+  build_meta(p, w0, nw, ht, nth, meta);
+  const int nhalf = do_move ? 2 : 1;
+  for (int h = ht; h < nw * R * nhalf; h += nth) {
+    const int i = do_move ? (h >> 1) : h;
+    const bool prop = do_move && (h & 1);
+    const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
+    prep_robot_half(p, w0 + wl, r, prop, wsb + (size_t)i * BRS_WS_STRIDE);
+    if (!prop) cflag[i] = make_int4(0, 0, 0, 0);
+  }
+  // the tile's wall store was requested before the robot state: by now it has usually landed
+  if (staged) mbar_wait(bar, parity);
+  build_segtab(p, nw, ht, nth, rawb, segtab);
 }
 
 // Direct-path sensors of one tile -- range sensors on their own mount, light sensors,
@@ -855,21 +940,18 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
 
 }
 
-// Robot.step of one tile by the helper team (thread ht of nth): PREP, then the
-// collision tests, then commit / stall and everything that hangs off the final pose.
-__device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
-                                                bool do_rays, bool do_sense, const uint32_t* __restrict__ rawb,
-                                                float4* __restrict__ segtab, double* __restrict__ wsb,
-                                                int4* __restrict__ cflag, int2* __restrict__ meta,
-                                                double2* __restrict__ org, GroupCull* __restrict__ gcull,
-                                                int* __restrict__ cq, float4* __restrict__ cpar, uint32_t bar,
-                                                uint32_t parity, bool staged) {
+// Robot.step of one tile after PREP, by a team of `nth` threads (index ht; barrier id
+// `bid`): the collision tests, then commit / stall and everything that hangs off the final
+// pose.  The fused kernel's helper team runs it a tile ahead of the workers; in the wide
+// path every thread of the CTA runs it at the start of its tile.
+__device__ BRS_INL_ROBOT void collide_commit_tile(const KParams& p, int w0, int nw, int ht, int nth, int bid,
+                                                    bool do_move, bool do_rays, bool do_direct,
+                                                    const uint32_t* __restrict__ rawb, float4* __restrict__ segtab,
+                                                    double* __restrict__ wsb, int4* __restrict__ cflag,
+                                                    int2* __restrict__ meta, double2* __restrict__ org,
+                                                    GroupCull* __restrict__ gcull, int* __restrict__ cq) {
   const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
   BRS_PH_DECL;
-  if (ht == 0) cq[0] = 0;  // candidate queue of the collision phase
-  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, cpar, bar, parity, staged);
-  team_sync(2, nth);
-  BRS_PH(ht == 0, 8);
   if (do_move) {
     // ---------------- COLLIDE ------------------------------------------------------
     // walls: GS threads per (world, robot) stride over its segments.  FP32 disc cull
@@ -892,7 +974,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
             const bool valid = item < total;
             const int i = valid ? (int)fdiv(item, p.dSC) : 0, j = valid ? item - i * SC : 0;
             const int wl = (int)fdiv(i, p.dR);
-            const float4 cp = cpar[i];
+            const float4 cp = *(const float4*)(wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_CPAR);
             const float4 s = segtab[(size_t)wl * nvis + j];
             const float ax = cp.x - s.x, ay = cp.y - s.y;
             const float ee = fmaf(s.z, s.z, s.w * s.w);
@@ -913,7 +995,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
             if (inside[k]) {
               const int i = it_i[k], j = it_j[k];
               const int pos = posb + __popc(bal & ((1u << lane) - 1u));
-              if (pos < BRS_CQ_MAX) {
+              if (pos < p.cq_max) {
                 cq[4 + pos] = (i << 16) | j;
               } else {  // queue full: test in place
                 const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
@@ -923,16 +1005,28 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
           }
         }
       }
-      team_sync(2, nth);
+      team_sync(bid, nth);
       BRS_PH(ht == 0, 9);
-      // pass 2: the queued (robot, wall) pairs, one per thread: FP32 edge classifier, then the
-      // exact FP64 test for what is not a certain miss
+      // pass 2: the queued (robot, wall) pairs, FOUR lanes per pair (one box edge each): FP32
+      // edge classifier, then the exact FP64 test of all four edges if any edge is not a
+      // certain miss -- the same tests as box_hits_wall, as a chain a quarter as long
       {
-        const int n = min(cq[0], BRS_CQ_MAX);
-        for (int c = ht; c < n; c += nth) {
-          const int e = cq[4 + c], i = e >> 16, j = e & 0xffff;
+        const int n = min(cq[0], p.cq_max);
+        const int e = ht & 3, e2 = (e + 1) & 3;
+        const uint32_t qm = 0xFu << ((ht & 31) & ~3);
+        for (int c = ht >> 2; c < n; c += nth >> 2) {
+          const int ent = cq[4 + c], i = ent >> 16, j = ent & 0xffff;
           const int wl = (int)fdiv(i, p.dR), r = i - wl * R;
-          if (box_hits_wall(p, wsb, rawb, segtab + (size_t)wl * nvis, i, j, wl, r, SC)) cflag[i].x = 1;
+          const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
+          const double ax = pr[2 * e], ay = pr[2 * e + 1], bx2 = pr[2 * e2], by2 = pr[2 * e2 + 1];
+          const bool maybe = edge_maybe_hits(p, pr, r, segtab[(size_t)wl * nvis + j], ax, ay, bx2, by2);
+          if (__ballot_sync(qm, maybe) & qm) {
+            const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
+            const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
+            const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
+            const bool hit = isect64_bool(ax, ay, ds(bx2, ax), ds(by2, ay), x3, y3, x4, y4);
+            if ((__ballot_sync(qm, hit) & qm) && e == 0) cflag[i].x = 1;
+          }
         }
       }
     BRS_PH(ht == 0, 10);
@@ -966,7 +1060,7 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
           if (hit) atomicOr(v ? &cflag[wl * R + ri].z : &cflag[wl * R + ri].y, 1 << ro);
         }
       }
-    team_sync(2, nth);
+    team_sync(bid, nth);
     BRS_PH(ht == 0, 11);
   }
   // ---------------- COMMIT ---------------------------------------------------------
@@ -1118,106 +1212,62 @@ __device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, 
   BRS_PH(ht == 0, 12);
   // camera worlds with a few extra sensors: the helper team has time to spare, the workers
   // do not -- run the direct-path sensors of this tile here, on the poses just committed
-  if (do_sense && p.direct_on_helper) {
-    team_sync(2, nth);
+  if (do_direct) {
+    team_sync(bid, nth);
     sense_direct(p, ht, nth, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta);
   }
   BRS_PH(ht == 0, 13);
 }
 
-template <int NR, bool BIG>
-__global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG ? BRS_BIG_CTAS : BRS_SMALL_CTAS)
-    brs_step_kernel(const __grid_constant__ KParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-  const int NW = p.NW;              // worker threads
-  const int NHT = NT - NW;          // helper team (>= 32)
-  const bool is_helper = tid >= NW;
-  const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
-  const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
-  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h, !BIG);
-  float4* const gtab = (float4*)(smem + L.gtab);
-  uint16_t* const gidx = (uint16_t*)(smem + L.gidx);
-  int2* const gcnt = (int2*)(smem + L.gcnt);
-  ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
-  Strip* const strips = (Strip*)(smem + L.strips);
-  double2* const camcs = (double2*)(smem + L.camcs);
-  uint32_t* const rowsky = (uint32_t*)(smem + L.rowsky);
-  uint32_t* const rowgnd = (uint32_t*)(smem + L.rowgnd);
-  uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
-  volatile int* const sched = (volatile int*)(smem + L.sched);
-  const int strips_per_col = 4 * (R - 1);
-  const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
-  const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
-  const bool do_rays = do_sense || do_cam;
-
-  // ---- prologue: the helper initialises the TMA barriers and goes straight to the first
-  // tile; the workers meanwhile load the camera tables (iteration -1 gives them nothing
-  // else to do), both meet at that iteration's barrier
-  if (tid == NW) {
-    mbar_init(smem_u32(&mbar[0]), 1);
-    mbar_init(smem_u32(&mbar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (!is_helper) {
-    for (int i = tid; i < p.n_camera * p.cam_w; i += NW) camcs[i] = p.cam_cs[i];
-    for (int i = tid; i < p.cam_h; i += NW) {
-      rowsky[i] = p.row_sky[i];
-      rowgnd[i] = p.row_gnd[i];
-    }
-  }
-
-  // paint mapping: worker thread -> (picture slot, row slot, column quad)
-  const int pQ = max(p.cam_w >> 2, 1), pQc = min(pQ, NW);  // pictures wider than 4 x NW: several quads per thread
-  const int p_q = tid % pQc, p_rest = tid / pQc, p_RS = p.paint_rs;
-  const int p_rslot = p_rest % p_RS, p_islot = p_rest / p_RS, p_nislot = (NW / pQc) / p_RS;
-
+// Robot.step of one tile by the fused kernel's helper team (thread ht of nth): PREP, then
+// the collision tests and the commit.
+__device__ BRS_INL_ROBOT void robot_step_tile(const KParams& p, int w0, int nw, int ht, int nth, bool do_move,
+                                                bool do_rays, bool do_sense, const uint32_t* __restrict__ rawb,
+                                                float4* __restrict__ segtab, double* __restrict__ wsb,
+                                                int4* __restrict__ cflag, int2* __restrict__ meta,
+                                                double2* __restrict__ org, GroupCull* __restrict__ gcull,
+                                                int* __restrict__ cq, uint32_t bar, uint32_t parity, bool staged) {
   BRS_PH_DECL;
-  // iteration -1 only lets the helper team step the CTA's first tile
-  int tile = 0;
-  for (int it = -1;; ++it) {
-    const int buf = it & 1;
-    const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
-    if (is_helper) {
-      // ================= helper team: Robot.step of the NEXT tile =====================
-      if (tid == NW) {
-        // next tile index + TMA of its wall store into the other buffer (free since the
-        // barrier that ended the previous iteration)
-        // (the first tile of a CTA is its block index; the counter hands out the rest)
-        const int tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
-        sched[1 + (buf ^ 1)] = tn;
-        if (!BIG && tn < p.n_tiles) {
-          const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-          mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
-          tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
-                       smem_u32(&mbar[buf ^ 1]));
-        }
-      }
-      team_sync(2, NHT);
-      const int tn = sched[1 + (buf ^ 1)];
-      if (tn < p.n_tiles) {
-        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-        // big worlds (one or two CTAs per SM by their tables alone) do not stage the wall
-        // store: the helper reads it once from L2 / HBM, coalesced, to build the FP32 table
-        const uint32_t* rawn = BIG ? p.seg + (size_t)wn * 5 * SC : (const uint32_t*)(smem + L.raw[buf ^ 1]);
-        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, do_sense, rawn,
-                        (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
-                        (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
-                        (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
-                        (int*)(smem + L.cq), (float4*)(smem + L.cpar), smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
-      }
-    } else if (do_rays && it >= 0) {
-      // ================= workers: sensors and pictures of THIS tile ====================
-      const uint32_t* const rawb = BIG ? p.seg + (size_t)w0 * 5 * SC : (const uint32_t*)(smem + L.raw[buf]);
-      const float4* const segtab = (const float4*)(smem + L.segtab[buf]);
-      const double* const wsb = (const double*)(smem + L.ws[buf]);
-      const int2* const meta = (const int2*)(smem + L.meta[buf]);
-      const double2* const org = (const double2*)(smem + L.org[buf]);
-      const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
-      // every thread observes the phase of this tile's wall store itself before reading it
-      if (!BIG) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
-      BRS_PH(tid == 0, 0);
+  if (ht == 0) cq[0] = 0;  // candidate queue of the collision phase
+  prepare_tile(p, w0, nw, ht, nth, do_move, rawb, segtab, wsb, cflag, meta, bar, parity, staged);
+  team_sync(2, nth);
+  BRS_PH(ht == 0, 8);
+  collide_commit_tile(p, w0, nw, ht, nth, 2, do_move, do_rays, do_sense && p.direct_on_helper, rawb, segtab, wsb, cflag,
+                      meta, org, gcull, cq);
+}
 
+// TABLE, SENSE and PAINT of one tile by a team of NW threads (index tid, barrier id 1).
+// `pm` is the thread's paint mapping.
+struct PaintMap {
+  int q, rslot, islot, nislot, RS;
+};
+__device__ __forceinline__ PaintMap make_paint_map(const KParams& p, int tid, int NW) {
+  // thread -> (picture slot, row slot, column quad); pictures wider than 4 x NW: several quads per thread
+  PaintMap m;
+  const int pQ = max(p.cam_w >> 2, 1), pQc = min(pQ, NW);
+  const int rest = tid / pQc;
+  m.q = tid % pQc;
+  m.RS = p.paint_rs;
+  m.rslot = rest % m.RS;
+  m.islot = rest / m.RS;
+  m.nislot = (NW / pQc) / m.RS;
+  return m;
+}
+template <int NR>
+__device__ __forceinline__ void sense_paint_tile(const KParams& p, const int tid, const int NW, const int lane,
+                                                 const int w0, const int nw, const bool do_sense, const bool do_cam,
+                                                 const bool direct_here, const uint32_t* __restrict__ rawb,
+                                                 const float4* __restrict__ segtab, const double* __restrict__ wsb,
+                                                 const int2* __restrict__ meta, const double2* __restrict__ org,
+                                                 const GroupCull* __restrict__ gcull, float4* __restrict__ gtab,
+                                                 uint16_t* __restrict__ gidx, int2* __restrict__ gcnt,
+                                                 ColInfo* __restrict__ colinfo, Strip* __restrict__ strips,
+                                                 const double2* __restrict__ camcs, const uint32_t* __restrict__ rowsky,
+                                                 const uint32_t* __restrict__ rowgnd, const PaintMap pm) {
+  const int R = p.n_robots, SC = p.seg_cap, NG = p.n_group, nvis = SC + 4 * R;
+  const int strips_per_col = 4 * (R - 1);
+  const int p_q = pm.q, p_rslot = pm.rslot, p_islot = pm.islot, p_nislot = pm.nislot, p_RS = pm.RS;
+  BRS_PH_DECL;
       // ---------------- TABLE ------------------------------------------------------------
       // per (world, group, visible segment): m = (ey, -ex)/na, q = d/na with d = O - P,
       // na = ex*dy - ey*dx.  Entries no ray of the group can hit are dropped: the own
@@ -1387,7 +1437,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         }
       }
       // 5b. direct path (unless the helper team already ran it for this tile)
-      if (do_sense && !p.direct_on_helper) sense_direct(p, tid, NW, lane, w0, nw, rawb, segtab, wsb, meta);
+      if (do_sense && direct_here) sense_direct(p, tid, NW, lane, w0, nw, rawb, segtab, wsb, meta);
 
       BRS_PH(tid == 0, 2);
       // ---------------- PAINT ----------------------------------------------------------------
@@ -1395,6 +1445,9 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         team_sync(1, NW);
       const int W = p.cam_w, H = p.cam_h, Q = W >> 2;
       const int nimg = nw * p.n_camera;
+      // aligned lane octets hold 8 adjacent quads of the same rows of one picture: the quad
+      // index of lane l is (tid % min(Q, NW)), so this needs Q (and NW) to be multiples of 8
+      const bool paint_oct = (Q & 7) == 0 && (NW & 7) == 0;
       uint4* const out0 = (uint4*)(p.cam_out + (size_t)w0 * p.n_camera * (size_t)H * W * 4);
       // worker thread -> (picture slot, row slot, column quad): the 4 column records stay
       // in registers over the rows, a warp writes whole 128-byte lines per store
@@ -1402,11 +1455,104 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         for (int im = p_islot; im < nimg; im += p_nislot)
           for (int q = p_q; q < Q; q += NW)
             paint_rows(out0 + (size_t)im * H * Q, colinfo + (size_t)im * W, strips + (size_t)im * W * strips_per_col,
-                       strips_per_col, rowsky, rowgnd, p.flat_rows != 0, q, Q, p_rslot, p_RS, H);
+                       strips_per_col, rowsky, rowgnd, p.flat_rows != 0, paint_oct, lane, q, Q, p_rslot, p_RS, H);
       }
       }
+  BRS_PH(tid == 0, 3);
+}
+
+template <int NR, bool BIG>
+__global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG ? BRS_BIG_CTAS : BRS_SMALL_CTAS)
+    brs_step_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int NW = p.NW;              // worker threads
+  const int NHT = NT - NW;          // helper team (>= 32)
+  const bool is_helper = tid >= NW;
+  const int R = p.n_robots, SC = p.seg_cap, TW = p.TW, NG = p.n_group;
+  const int nvis = SC + 4 * R;  // table stride per world: walls, then 4 edges per robot at S + 4*o + e
+  const SmemLayout L = make_layout(TW, SC, R, NG, p.n_camera, p.cam_w, p.cam_h, !BIG);
+  float4* const gtab = (float4*)(smem + L.gtab);
+  uint16_t* const gidx = (uint16_t*)(smem + L.gidx);
+  int2* const gcnt = (int2*)(smem + L.gcnt);
+  ColInfo* const colinfo = (ColInfo*)(smem + L.colinfo);
+  Strip* const strips = (Strip*)(smem + L.strips);
+  double2* const camcs = (double2*)(smem + L.camcs);
+  uint32_t* const rowsky = (uint32_t*)(smem + L.rowsky);
+  uint32_t* const rowgnd = (uint32_t*)(smem + L.rowgnd);
+  uint64_t* const mbar = (uint64_t*)(smem + L.mbar);
+  volatile int* const sched = (volatile int*)(smem + L.sched);
+  const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
+  const bool do_move = p.flags & 1u, do_sense = p.flags & 2u, do_cam = (p.flags & 4u) && p.n_camera > 0;
+  const bool do_rays = do_sense || do_cam;
+
+  // ---- prologue: the helper initialises the TMA barriers and goes straight to the first
+  // tile; the workers meanwhile load the camera tables (iteration -1 gives them nothing
+  // else to do), both meet at that iteration's barrier
+  if (tid == NW) {
+    mbar_init(smem_u32(&mbar[0]), 1);
+    mbar_init(smem_u32(&mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (!is_helper) {
+    for (int i = tid; i < p.n_camera * p.cam_w; i += NW) camcs[i] = p.cam_cs[i];
+    for (int i = tid; i < p.cam_h; i += NW) {
+      rowsky[i] = p.row_sky[i];
+      rowgnd[i] = p.row_gnd[i];
     }
-    BRS_PH(tid == 0, 3);
+  }
+
+  const PaintMap pmap = make_paint_map(p, tid, NW);
+
+  BRS_PH_DECL;
+  // iteration -1 only lets the helper team step the CTA's first tile
+  int tile = 0;
+  for (int it = -1;; ++it) {
+    const int buf = it & 1;
+    const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
+    if (is_helper) {
+      // ================= helper team: Robot.step of the NEXT tile =====================
+      if (tid == NW) {
+        // next tile index + TMA of its wall store into the other buffer (free since the
+        // barrier that ended the previous iteration)
+        // (the first tile of a CTA is its block index; the counter hands out the rest)
+        const int tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
+        sched[1 + (buf ^ 1)] = tn;
+        if (!BIG && tn < p.n_tiles) {
+          const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
+          mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
+          tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
+                       smem_u32(&mbar[buf ^ 1]));
+        }
+      }
+      team_sync(2, NHT);
+      const int tn = sched[1 + (buf ^ 1)];
+      if (tn < p.n_tiles) {
+        const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
+        // big worlds (one or two CTAs per SM by their tables alone) do not stage the wall
+        // store: the helper reads it once from L2 / HBM, coalesced, to build the FP32 table
+        const uint32_t* rawn = BIG ? p.seg + (size_t)wn * 5 * SC : (const uint32_t*)(smem + L.raw[buf ^ 1]);
+        robot_step_tile(p, wn, nn, tid - NW, NHT, do_move, do_rays, do_sense, rawn,
+                        (float4*)(smem + L.segtab[buf ^ 1]), (double*)(smem + L.ws[buf ^ 1]),
+                        (int4*)(smem + L.cflag[buf ^ 1]), (int2*)(smem + L.meta[buf ^ 1]),
+                        (double2*)(smem + L.org[buf ^ 1]), (GroupCull*)(smem + L.gcull[buf ^ 1]),
+                        (int*)(smem + L.cq), smem_u32(&mbar[buf ^ 1]), (uint32_t)((it + 1) >> 1) & 1u, !BIG);
+      }
+    } else if (do_rays && it >= 0) {
+      // ================= workers: sensors and pictures of THIS tile ====================
+      const uint32_t* const rawb = BIG ? p.seg + (size_t)w0 * 5 * SC : (const uint32_t*)(smem + L.raw[buf]);
+      const float4* const segtab = (const float4*)(smem + L.segtab[buf]);
+      const double* const wsb = (const double*)(smem + L.ws[buf]);
+      const int2* const meta = (const int2*)(smem + L.meta[buf]);
+      const double2* const org = (const double2*)(smem + L.org[buf]);
+      const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
+      // every thread observes the phase of this tile's wall store itself before reading it
+      if (!BIG) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+      BRS_PH(tid == 0, 0);
+
+      sense_paint_tile<NR>(p, tid, NW, lane, w0, nw, do_sense, do_cam, !p.direct_on_helper, rawb, segtab, wsb, meta, org,
+                           gcull, gtab, gidx, gcnt, colinfo, strips, camcs, rowsky, rowgnd, pmap);
+    }
     BRS_PH(tid == NW, 14);
     __syncthreads();  // the teams meet: this tile is done, the next one is stepped
     tile = sched[1 + (buf ^ 1)];

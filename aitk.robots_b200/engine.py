@@ -228,9 +228,12 @@ class BatchEngine:
         cabi.check(self._lib.brs_launch_info(self._h, C.byref(t), C.byref(c), C.byref(s), C.byref(m)))
         tw, nt, nw, nr, ng = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         cabi.check(self._lib.brs_tile_info(self._h, C.byref(tw), C.byref(nt), C.byref(nw), C.byref(nr), C.byref(ng)))
-        return {"threads": t.value, "ctas": c.value, "smem_bytes": s.value, "sm_count": m.value,
-                "worlds_per_tile": tw.value, "tiles": nt.value, "workers": nw.value, "cols_per_thread": nr.value,
-                "ray_groups": ng.value}
+        wide, nl = C.c_int(), C.c_int()
+        cabi.check(self._lib.brs_path_info(self._h, C.byref(wide), C.byref(nl)))
+        return {"path": "wide (prep + step kernel, PDL)" if wide.value else "fused (one kernel)",
+                "launches_per_step": nl.value, "threads": t.value, "ctas": c.value, "smem_bytes": s.value,
+                "sm_count": m.value, "worlds_per_tile": tw.value, "tiles": nt.value, "workers": nw.value,
+                "cols_per_thread": nr.value, "ray_groups": ng.value}
 
     def synchronize(self, stream=0):
         cabi.check(self._lib.brs_synchronize(self._h, stream))

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define BRS_ABI_VERSION 2
+#define BRS_ABI_VERSION 3
 #define BRS_MAX_ROBOTS 8 /* robots per world */
 
 typedef enum brs_status {
@@ -191,6 +191,13 @@ int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem_bytes, int
  * brs_launch_info = workers + one helper warp), camera columns per worker
  * thread, shared-origin ray groups per world. */
 int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* workers, int* cols_per_thread, int* n_groups);
+
+/* Which of the two launch plans brs_create chose for this engine (for reports and tests):
+ * *wide = 0: the fused kernel (one launch per step; Robot.step of tile n+1 overlaps the rays
+ * of tile n inside a CTA), 1: the wide path (prep kernel + step kernel chained with
+ * programmatic dependent launch; see csrc/brs_wide.cuh).  Both produce identical bits.
+ * *launches_per_step = kernels one brs_step enqueues. */
+int brs_path_info(brs_engine* e, int* wide, int* launches_per_step);
 
 /* FP32 FFMA throughput microbenchmark on the engine's device: runs `iters`
  * dependent-chain FFMA sweeps on every SM and returns TFLOP/s (2 flop / FFMA)

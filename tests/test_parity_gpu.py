@@ -178,10 +178,19 @@ def test_culling_and_tiling_never_change_results(maker):
     """Cone / range culling, table compaction, tile size and launch shape only remove or
     regroup work: every output is bit-identical with them switched off or changed."""
     scene = maker()
-    base = _outputs(scene, 3, {})
-    for env in ({"BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_TW": "1"}, {"BRS_TW": "5", "BRS_BIG": "1"},
-                {"BRS_NH": "2"}, {"BRS_DIRECT_ON_HELPER": "1"}, {"BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
-                {"BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
+    # the base run is the fused kernel; BRS_WIDE=1 variants run the two-kernel wide path
+    # (one-warp teams, wider teams, several worlds per tile, walls from L2, no PDL)
+    base = _outputs(scene, 3, {"BRS_WIDE": "0"})
+    for env in ({"BRS_WIDE": "0", "BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_WIDE": "0", "BRS_TW": "1"},
+                {"BRS_WIDE": "0", "BRS_TW": "5", "BRS_BIG": "1"},
+                {"BRS_WIDE": "0", "BRS_NH": "2"}, {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "1"},
+                {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
+                {"BRS_WIDE": "0", "BRS_NR": "1", "BRS_GROUP_MIN": "1000"},
+                {"BRS_WIDE": "1"}, {"BRS_WIDE": "1", "BRS_WNT": "32", "BRS_WTW": "1"},
+                {"BRS_WIDE": "1", "BRS_WNT": "32", "BRS_WTW": "3"}, {"BRS_WIDE": "1", "BRS_WNT": "96", "BRS_WTW": "2"},
+                {"BRS_WIDE": "1", "BRS_WNT": "256", "BRS_WTW": "5", "BRS_WBIG": "1"},
+                {"BRS_WIDE": "1", "BRS_PDL": "0", "BRS_NO_CONE": "1"},
+                {"BRS_WIDE": "1", "BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
         other = _outputs(scene, 3, env)
         for k in base:
             if k in ("range", "light") and env.get("BRS_GROUP_MIN"):
