@@ -127,6 +127,7 @@ SYMBOLS = [
     ("brs_upload", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     ("brs_download", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     ("brs_step", C.c_int, [_P, C.c_double, C.c_uint, _P]),
+    ("brs_step_counted", C.c_int, [_P, C.c_double, C.c_uint, _P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     ("brs_step_host", C.c_int, [_P, C.c_double, C.c_uint, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("brs_synchronize", C.c_int, [_P, _P]),
     ("brs_count_tests", C.c_int, [_P, C.c_uint, _P, C.POINTER(C.c_ulonglong)]),

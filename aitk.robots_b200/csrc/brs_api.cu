@@ -55,6 +55,8 @@ struct brs_engine {
   int flat_rows = 1;
   unsigned int* d_sched = nullptr;
   unsigned long long* d_phase = nullptr;  // BRS_PHASE_TIMING builds
+  unsigned long long* d_counters = nullptr;  // [2] executed-work counters (brs_step_counted)
+  bool counting = false;
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
@@ -67,6 +69,7 @@ struct brs_engine {
   double* d_ws = nullptr;  // [B][R][BRS_WS_STRIDE] robot records between the two kernels
   int wNT = 32, wTW = 1, wSLG = 1, wSLD = 1, wSLL = 1, w_paint_rs = 1, w_tiles = 1, w_grid = 1, w_smem = 0, w_fused_table = 1;
   bool w_big = false, pdl = true;
+  bool prep_fused = false;  // fused kernel fed by brs_prep_kernel (two launches)
   const void* w_kfn = nullptr;
 };
 
@@ -312,6 +315,11 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
           range = std::fmax(range, gdev[i].max);
         }
       GroupDev& g = groups[k];
+      g.cam_rays = g.range_rays = 0;
+      for (int i = 0; i < cfg->n_camera; ++i)
+        if (cdev[i].group == (int)k) g.cam_rays += e->cameras[i].width;
+      for (int i = 0; i < cfg->n_range; ++i)
+        if (gdev[i].group == (int)k) g.range_rays += gdev[i].n_rays;
       g.range = (float)(range * (1.0 + 1e-4) + 1e-3);
       g.has_cone = 0;
       // smallest arc containing all directions: try every direction as the arc's start
@@ -585,6 +593,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     const bool auto_wide = cfg->n_worlds >= env_int("BRS_WIDE_MIN_WORLDS", 16384);
     e->wide = wide_ok && env_int("BRS_WIDE", auto_wide ? 1 : 0) != 0;
     e->pdl = env_int("BRS_PDL", 1) != 0;
+    e->prep_fused = wide_ok && !e->wide && env_int("BRS_PREP", 0) != 0;
     if (wide_ok) {
       const size_t bytes = (size_t)cfg->n_worlds * R * BRS_WS_STRIDE * 8 + 64;
       ce = cudaMalloc((void**)&e->d_ws, bytes);
@@ -634,6 +643,7 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_rowsky);
   cudaFree(e->d_rowgnd);
   cudaFree(e->d_ws);
+  cudaFree(e->d_counters);
   delete e;
   return BRS_OK;
 }
@@ -708,6 +718,7 @@ static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned fl
     p.fused_table = e->fused_table;
     p.NW = e->NW; p.NH = e->NH;
     p.cq_max = BRS_CQ_MAX;
+    p.prepped = e->prep_fused ? 1 : 0;
   }
   {
     const int R = c.n_robots, nvis = c.seg_cap + 4 * R;
@@ -744,6 +755,7 @@ static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned fl
   p.sched = e->d_sched;
   p.phase = e->d_phase;
   p.wsg = e->d_ws;
+  p.counters = e->counting ? e->d_counters : nullptr;
 }
 
 extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
@@ -753,7 +765,7 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   KParams p;
   fill_params(e, p, time_step, flags, e->wide);
   void* args[] = {(void*)&p};
-  if (!e->wide) {
+  if (!e->wide && !e->prep_fused) {
     CK(cudaLaunchKernel(e->kfn, dim3(e->grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
   } else {
     // prep (thread per robot half), then the step kernel under programmatic dependent launch:
@@ -762,18 +774,36 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
     CK(cudaLaunchKernel((const void*)brs_prep_kernel, dim3((halves + 255u) / 256u), dim3(256), args, 0, (cudaStream_t)stream));
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(e->w_grid);
-    lc.blockDim = dim3(e->wNT);
-    lc.dynamicSmemBytes = (size_t)e->w_smem;
+    lc.gridDim = dim3(e->wide ? e->w_grid : e->grid);
+    lc.blockDim = dim3(e->wide ? e->wNT : e->T);
+    lc.dynamicSmemBytes = (size_t)(e->wide ? e->w_smem : e->smem);
     lc.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
     lc.attrs = at;
     lc.numAttrs = 1;
-    CK(cudaLaunchKernelExC(&lc, e->w_kfn, args));
+    CK(cudaLaunchKernelExC(&lc, e->wide ? e->w_kfn : e->kfn, args));
   }
   CK(cudaGetLastError());
+  return BRS_OK;
+}
+
+extern "C" int brs_step_counted(brs_engine* e, double time_step, unsigned flags, void* stream,
+                                unsigned long long* ray_tests, unsigned long long* edge_tests) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_step_counted: null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  if (!e->d_counters) CK(cudaMalloc((void**)&e->d_counters, 16));
+  CK(cudaMemsetAsync(e->d_counters, 0, 16, (cudaStream_t)stream));
+  e->counting = true;
+  const int rc = brs_step(e, time_step, flags, stream);
+  e->counting = false;
+  if (rc) return rc;
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, e->d_counters, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (ray_tests) *ray_tests = h[0];
+  if (edge_tests) *edge_tests = h[1];
   return BRS_OK;
 }
 
@@ -832,8 +862,8 @@ extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem
 
 extern "C" int brs_path_info(brs_engine* e, int* wide, int* launches_per_step) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_path_info: null engine");
-  if (wide) *wide = e->wide ? 1 : 0;
-  if (launches_per_step) *launches_per_step = e->wide ? 2 : 1;
+  if (wide) *wide = e->wide ? 1 : (e->prep_fused ? 2 : 0);
+  if (launches_per_step) *launches_per_step = (e->wide || e->prep_fused) ? 2 : 1;
   return BRS_OK;
 }
 

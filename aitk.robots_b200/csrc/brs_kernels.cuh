@@ -95,7 +95,9 @@ struct GroupDev {  // rays sharing one origin: robot + mount offset, and what th
   // unit vectors of its lower / upper boundary and of its axis (has_cone: width < 180 deg)
   float lo_c, lo_s, hi_c, hi_s, ax_c, ax_s;
   float range;  // longest ray of the group, widened by a margin
-  float _pad;
+  int cam_rays;    // camera columns that search this group's table (walls only)
+  int range_rays;  // range-sensor rays that search it (walls and robots)
+  int _pad;
 };
 struct __align__(16) GroupCull {  // per (world, group), world frame
   float lo_x, lo_y, hi_x, hi_y, ax_x, ax_y, range2;
@@ -130,6 +132,7 @@ struct KParams {
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
   int NH;            // helper warps: Robot.step of the next tile while the workers sense and paint this one
+  int prepped;       // fused kernel: the robot records come from brs_prep_kernel (TMA from p.wsg) instead of PREP on the helper
   int cq_max;        // capacity of the collision candidate queue (<= BRS_CQ_MAX; overflow is tested in place)
   FastDiv dR, dSC, dSQ, dTab, dNvis, dPair, dGT, dDT, dLT, dST, dCpb, dNG;
   unsigned flags;
@@ -162,6 +165,10 @@ struct KParams {
   unsigned int* sched;      // [2] next tile, finished CTAs (self-resetting)
   unsigned long long* phase;  // [16] cycle sums per phase (builds with -DBRS_PHASE_TIMING), else unused
   double* wsg;              // [B][R][BRS_WS_STRIDE] robot records of the wide path (prep kernel -> step kernel)
+  // [2] or NULL: EXECUTED work of this launch (brs_step_counted): [0] ray-segment tests the
+  // search loops ran (table entries that survived the culls x rays, direct-path segments x
+  // rays), [1] box-edge-vs-wall tests the collision classifier ran (4 per disc candidate)
+  unsigned long long* counters;
 };
 
 // per-column paint record
@@ -815,6 +822,15 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
                                              double* __restrict__ wsb, int4* __restrict__ cflag,
                                              int2* __restrict__ meta, uint32_t bar, uint32_t parity, bool staged) {
   const int R = p.n_robots;
+  if (p.prepped) {
+    // the robot records (and the per-world meta inside them) were computed by brs_prep_kernel
+    // and arrive with the walls through the same TMA barrier
+    for (int i = ht; i < nw * R; i += nth) cflag[i] = make_int4(0, 0, 0, 0);
+    mbar_wait(bar, parity);
+    for (int wl = ht; wl < nw; wl += nth) meta[wl] = *(const int2*)(wsb + (size_t)wl * R * BRS_WS_STRIDE + BRS_WS_META);
+    build_segtab(p, nw, ht, nth, rawb, segtab);
+    return;
+  }
   // per-world meta first: its global loads overlap the float64 chain below
   build_meta(p, w0, nw, ht, nth, meta);
   const int nhalf = do_move ? 2 : 1;
@@ -878,7 +894,10 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
       }
       // (upstream stores reading = d / max and returns reading * max: the float32
       //  observation cannot see that round trip)
-      if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
+      if (g == 0) {
+        p.range_out[(size_t)w * p.n_range + si] = (float)best;
+        if (p.counters) atomicAdd(&p.counters[0], (unsigned long long)sd.n_rays * (nseg - 4));
+      }
     }
   }
   // ... light sensors: line of sight to every bulb ...
@@ -916,7 +935,10 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
         }
         if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
       }
-      if (g == 0) p.light_out[(size_t)w * p.n_light + li] = (float)value;
+      if (g == 0) {
+        p.light_out[(size_t)w * p.n_light + li] = (float)value;
+        if (p.counters) atomicAdd(&p.counters[0], (unsigned long long)p.n_bulbs * (nseg - 4));
+      }
     }
   }
   // ... smell sensors: grid lookup at the mount point
@@ -1020,6 +1042,7 @@ __device__ BRS_INL_ROBOT void collide_commit_tile(const KParams& p, int w0, int 
           const double* pr = wsb + (size_t)i * BRS_WS_STRIDE + BRS_WS_PROP;
           const double ax = pr[2 * e], ay = pr[2 * e + 1], bx2 = pr[2 * e2], by2 = pr[2 * e2 + 1];
           const bool maybe = edge_maybe_hits(p, pr, r, segtab[(size_t)wl * nvis + j], ax, ay, bx2, by2);
+          if (p.counters && e == 0) atomicAdd(&p.counters[1], 4ull);
           if (__ballot_sync(qm, maybe) & qm) {
             const uint32_t* raw = rawb + (size_t)wl * 5 * SC;
             const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
@@ -1302,7 +1325,12 @@ __device__ __forceinline__ void sense_paint_tile(const KParams& p, const int tid
             cw += __popc(nwall >= 32 ? bal : (nwall <= 0 ? 0u : (bal & ((1u << nwall) - 1u))));
             base += __popc(bal);
           }
-          if (lane == 0) gcnt[pg] = make_int2(cw, base);
+          if (lane == 0) {
+            gcnt[pg] = make_int2(cw, base);
+            if (p.counters)
+              atomicAdd(&p.counters[0], (unsigned long long)cw * (do_cam ? p.groups[g].cam_rays : 0) +
+                                            (unsigned long long)base * (do_sense ? p.groups[g].range_rays : 0));
+          }
         }
         team_sync(1, NW);
       } else if (NG > 0) {
@@ -1345,7 +1373,13 @@ __device__ __forceinline__ void sense_paint_tile(const KParams& p, const int tid
               cw += __popc(nwall >= 32 ? bal : (nwall <= 0 ? 0u : (bal & ((1u << nwall) - 1u))));
               base += __popc(bal);
             }
-            if (lane == 0) gcnt[pg] = make_int2(cw, base);
+            if (lane == 0) {
+              gcnt[pg] = make_int2(cw, base);
+              const GroupDev& gd = p.groups[pg - wl * NG];
+              if (p.counters)
+                atomicAdd(&p.counters[0], (unsigned long long)cw * (do_cam ? gd.cam_rays : 0) +
+                                              (unsigned long long)base * (do_sense ? gd.range_rays : 0));
+            }
           }
         }
         team_sync(1, NW);
@@ -1503,6 +1537,8 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
   }
 
   const PaintMap pmap = make_paint_map(p, tid, NW);
+  // launched behind brs_prep_kernel (programmatic dependent launch): nothing below may pass it
+  if (p.prepped) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   BRS_PH_DECL;
   // iteration -1 only lets the helper team step the CTA's first tile
@@ -1518,11 +1554,16 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         // (the first tile of a CTA is its block index; the counter hands out the rest)
         const int tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
         sched[1 + (buf ^ 1)] = tn;
-        if (!BIG && tn < p.n_tiles) {
+        if ((!BIG || p.prepped) && tn < p.n_tiles) {
           const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
-          mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), nn * world_bytes);
-          tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
-                       smem_u32(&mbar[buf ^ 1]));
+          const uint32_t robot_bytes = p.prepped ? (uint32_t)(nn * R * BRS_WS_STRIDE * 8) : 0u;
+          mbar_expect_tx(smem_u32(&mbar[buf ^ 1]), (BIG ? 0u : nn * world_bytes) + robot_bytes);
+          if (!BIG)
+            tma_bulk_g2s(smem_u32(smem + L.raw[buf ^ 1]), p.seg + (size_t)wn * 5 * SC, nn * world_bytes,
+                         smem_u32(&mbar[buf ^ 1]));
+          if (p.prepped)
+            tma_bulk_g2s(smem_u32(smem + L.ws[buf ^ 1]), p.wsg + (size_t)wn * R * BRS_WS_STRIDE, robot_bytes,
+                         smem_u32(&mbar[buf ^ 1]));
         }
       }
       team_sync(2, NHT);
@@ -1547,7 +1588,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       const double2* const org = (const double2*)(smem + L.org[buf]);
       const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
       // every thread observes the phase of this tile's wall store itself before reading it
-      if (!BIG) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+      if (!BIG || p.prepped) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
       BRS_PH(tid == 0, 0);
 
       sense_paint_tile<NR>(p, tid, NW, lane, w0, nw, do_sense, do_cam, !p.direct_on_helper, rawb, segtab, wsb, meta, org,

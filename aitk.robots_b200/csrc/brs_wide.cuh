@@ -161,16 +161,26 @@ __global__ void __launch_bounds__(NT_MAX, MIN_CTAS) brs_wide_kernel(const __grid
   const PaintMap pmap = make_paint_map(p, tid, NT);
   team_sync(0, NT);
   int tile = (int)blockIdx.x;  // the first tile of a CTA is its block index; the counter hands out the rest
-  if (tid == 0 && tile < p.n_tiles) request_tile(tile, 0, true);
+  // Tickets run TWO tiles ahead: the atomic for tile it+2 is issued at the start of tile it and
+  // consumed at the start of tile it+1, so its round trip to L2 never stalls the team.
+  unsigned ticket = 0;
+  if (tid == 0) {
+    ticket = atomicAdd(&p.sched[0], 1u);
+    if (tile < p.n_tiles) request_tile(tile, 0, true);
+  }
   griddep_wait();  // every thread: nothing below may pass the prep kernel (it reads the poses COMMIT writes)
 
   for (int it = 0; tile < p.n_tiles; ++it) {
     const int buf = it & 1;
     const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
-    // next tile: the counter's atomic is issued now and consumed after BUILD, so that its
-    // round trip to L2 never stalls the team
-    unsigned ticket = 0;
-    if (tid == 0) ticket = atomicAdd(&p.sched[0], 1u);
+    if (tid == 0) {
+      // next tile: its walls and records go to the other buffer (free since the barrier that
+      // ended the previous tile)
+      const int tn = (int)(gridDim.x + ticket);
+      sched[buf ^ 1] = tn;
+      if (tn < p.n_tiles) request_tile(tn, buf ^ 1, false);
+      ticket = atomicAdd(&p.sched[0], 1u);
+    }
     const uint32_t* const rawb = BIG ? p.seg + (size_t)w0 * 5 * SC : (const uint32_t*)(smem + L.raw[buf]);
     double* const wsb = (double*)(smem + L.ws[buf]);
     // ---------------- BUILD: per-world meta, collision flags, FP32 wall table ----------
@@ -179,12 +189,6 @@ __global__ void __launch_bounds__(NT_MAX, MIN_CTAS) brs_wide_kernel(const __grid
     mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
     for (int wl = tid; wl < nw; wl += NT) meta[wl] = *(const int2*)(wsb + (size_t)wl * R * BRS_WS_STRIDE + BRS_WS_META);
     build_segtab(p, nw, tid, NT, rawb, segtab);
-    if (tid == 0) {
-      // ... its TMA into the other buffer (free since the barrier that ended the previous tile)
-      const int tn = (int)(gridDim.x + ticket);
-      sched[buf ^ 1] = tn;
-      if (tn < p.n_tiles) request_tile(tn, buf ^ 1, false);
-    }
     team_sync(0, NT);
     // ---------------- COLLIDE + COMMIT ----------------------------------------------------
     collide_commit_tile(p, w0, nw, tid, NT, 0, do_move, do_rays, false, rawb, segtab, wsb, cflag, meta, org, gcull, cq);
@@ -200,6 +204,9 @@ __global__ void __launch_bounds__(NT_MAX, MIN_CTAS) brs_wide_kernel(const __grid
 
   // self-resetting scheduler: the last CTA to leave zeroes both counters for the next launch
   if (tid == 0) {
+    // (the CTA's last ticket was never consumed: depend on it, so that its atomic has been
+    //  performed before this CTA counts as finished and the counters can be reset)
+    if (ticket == 0xFFFFFFFFu) p.sched[1] = 0u;
     __threadfence();
     const unsigned done = atomicAdd(&p.sched[1], 1u);
     if (done == gridDim.x - 1) {

@@ -153,14 +153,14 @@ class BatchEngine:
         n = a.shape[0]
         assert a.shape[1:] == tuple(tail(self)), (name, a.shape, tail(self))
         cabi.check(self._lib.brs_upload(self._h, bid, a.ctypes.data, first_world, n, stream))
-        self.synchronize()  # pageable source: keep `a` alive until the copy is done
+        self.synchronize(stream)  # pageable source: keep `a` alive until the copy is done
 
     def download(self, name, first_world=0, n_worlds=None, stream=0):
         bid, dtype, tail = _BUF_META[name]
         n = self.n_worlds - first_world if n_worlds is None else n_worlds
         out = np.empty((n,) + tuple(tail(self)), dtype=dtype)
         cabi.check(self._lib.brs_download(self._h, bid, out.ctypes.data, first_world, n, stream))
-        self.synchronize()
+        self.synchronize(stream)
         return out
 
     def device_ptr(self, name):
@@ -218,6 +218,14 @@ class BatchEngine:
                                     smell, stream)
         )
 
+    def step_counted(self, time_step=None, flags=cabi.STEP_ALL, stream=0):
+        """One real step with the executed work counted on the device:
+        (ray-segment tests the search loops ran, box-edge tests the collision classifier ran)."""
+        dt = self.time_step if time_step is None else time_step
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        cabi.check(self._lib.brs_step_counted(self._h, float(dt), int(flags), stream, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def count_tests(self, flags=cabi.STEP_ALL, stream=0):
         n = C.c_ulonglong()
         cabi.check(self._lib.brs_count_tests(self._h, int(flags), stream, C.byref(n)))
@@ -230,7 +238,7 @@ class BatchEngine:
         cabi.check(self._lib.brs_tile_info(self._h, C.byref(tw), C.byref(nt), C.byref(nw), C.byref(nr), C.byref(ng)))
         wide, nl = C.c_int(), C.c_int()
         cabi.check(self._lib.brs_path_info(self._h, C.byref(wide), C.byref(nl)))
-        return {"path": "wide (prep + step kernel, PDL)" if wide.value else "fused (one kernel)",
+        return {"path": ("fused (one kernel)", "wide (prep + step kernel, PDL)", "fused fed by the prep kernel (PDL)")[wide.value],
                 "launches_per_step": nl.value, "threads": t.value, "ctas": c.value, "smem_bytes": s.value,
                 "sm_count": m.value, "worlds_per_tile": tw.value, "tiles": nt.value, "workers": nw.value,
                 "cols_per_thread": nr.value, "ray_groups": ng.value}

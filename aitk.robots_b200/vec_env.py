@@ -53,11 +53,16 @@ class VecEnv:
                                    dtype=torch.float64, device=dev)  # [R, 2]
         self.steps = torch.zeros(self.n_worlds, dtype=torch.int64, device=dev)
         self._prev_xy = self.pose[..., :2].clone()
-        self.stream = torch.cuda.current_stream(dev)
+        self._dev = dev
 
     # -- helpers -------------------------------------------------------------------
+    def _stream(self):
+        # the caller's CURRENT stream at the time of the call (torch.cuda.stream(...) contexts
+        # change it), so that the launch is ordered with the torch ops around it
+        return self.torch.cuda.current_stream(self._dev).cuda_stream
+
     def _sense(self):
-        self.engine.step(flags=self.flags & ~cabi.STEP_MOVE, stream=self.stream.cuda_stream)
+        self.engine.step(flags=self.flags & ~cabi.STEP_MOVE, stream=self._stream())
 
     def observations(self):
         """Dict of zero-copy observation tensors (valid until the next step)."""
@@ -85,7 +90,7 @@ class VecEnv:
         self.target_vel[..., 0] = a[..., 0] * self._scale[:, 0]
         self.target_vel[..., 2] = a[..., 1] * self._scale[:, 1]
         self._prev_xy.copy_(self.pose[..., :2])
-        self.engine.step(flags=self.flags, stream=self.stream.cuda_stream)  # the one kernel launch
+        self.engine.step(flags=self.flags, stream=self._stream())  # the step launch
         self.steps += 1
         if self.reward_fn is not None:
             reward = self.reward_fn(self)
@@ -93,7 +98,8 @@ class VecEnv:
             moved = (self.pose[..., :2] - self._prev_xy).norm(dim=-1).sum(dim=1)
             reward = (moved - self.stall_penalty * self.stalled.to(t.float64).sum(dim=1)).to(t.float32)
         done = self.done_fn(self) if self.done_fn is not None else self.steps >= self.max_steps
-        info = {"stalled": self.stalled, "steps": self.steps.clone()}
+        # (copies: the reset below clears the live views for the worlds that just finished)
+        info = {"stalled": self.stalled.clone(), "steps": self.steps.clone()}
         if bool(done.any()):
             self.reset(done)  # finished worlds restart; their new observations are already sensed
         return self.obs, reward, done, info

@@ -18,6 +18,30 @@ from .scenes import CameraSpec, LightSpec, RangeSpec, RobotSpec, SceneBatch, Sme
 
 PI_OVER_180 = math.pi / 180.0
 
+
+class FacadeDefaults:
+    """Constants of the public API that never reach the kernel and are recollected, NOT
+    verified against upstream aitk.  They are named here --
+    and mirrored by ``oracle.aitk_oracle.Switches`` under the same names -- so that the day
+    the real package is seen they are flipped in one place."""
+
+    # Robot(max_rotate_velocity=...): radians per second at rotate == 1            [unverified]
+    ROBOT_MAX_ROTATE_VELOCITY = math.pi / 4
+    # Robot(max_trans_velocity=...): world units per step at translate == 1       [unverified]
+    ROBOT_MAX_TRANS_VELOCITY = 2.0
+    # Robot.move(): upstream may round the target velocities (e.g. to 1 decimal); None = no rounding  [unverified]
+    MOVE_ROUND_DIGITS = None
+    # Camera(a=...): default field of view in degrees                               [unverified]
+    CAMERA_DEFAULT_FOV = 60
+    # Camera(width, height) defaults                                                [unverified]
+    CAMERA_DEFAULT_SIZE = (64, 32)
+
+
+def _round_target(v):
+    d = FacadeDefaults.MOVE_ROUND_DIGITS
+    return v if d is None else round(v, d)
+
+
 COLORS = {
     "black": (0, 0, 0), "white": (255, 255, 255), "red": (255, 0, 0), "green": (0, 128, 0),
     "lime": (0, 255, 0), "blue": (0, 0, 255), "yellow": (255, 255, 0), "cyan": (0, 255, 255),
@@ -67,9 +91,12 @@ class RangeSensor(_Device):
 
 
 class Camera(_Device):
-    def __init__(self, width=64, height=32, a=60, colorsFadeWithDistance=0.9, sizeFadeWithDistance=1.0,
+    def __init__(self, width=None, height=None, a=None, colorsFadeWithDistance=0.9, sizeFadeWithDistance=1.0,
                  max_range=1000, position=(0, 0), name="camera"):
         super().__init__()
+        width = FacadeDefaults.CAMERA_DEFAULT_SIZE[0] if width is None else width
+        height = FacadeDefaults.CAMERA_DEFAULT_SIZE[1] if height is None else height
+        a = FacadeDefaults.CAMERA_DEFAULT_FOV if a is None else a
         self.spec = CameraSpec(width=int(width), height=int(height), a=float(a),
                                colorsFadeWithDistance=float(colorsFadeWithDistance),
                                sizeFadeWithDistance=float(sizeFadeWithDistance), max_range=float(max_range),
@@ -123,8 +150,12 @@ class Bulb:
 class Robot:
     """Robot(x, y, a) with ``a`` in degrees, as upstream."""
 
-    def __init__(self, x=0, y=0, a=0, color="red", name="Robbie", height=0.25, max_trans_velocity=2.0,
-                 max_rotate_velocity=math.pi / 4, bbox=None):
+    def __init__(self, x=0, y=0, a=0, color="red", name="Robbie", height=0.25, max_trans_velocity=None,
+                 max_rotate_velocity=None, bbox=None):
+        if max_trans_velocity is None:
+            max_trans_velocity = FacadeDefaults.ROBOT_MAX_TRANS_VELOCITY
+        if max_rotate_velocity is None:
+            max_rotate_velocity = FacadeDefaults.ROBOT_MAX_ROTATE_VELOCITY
         self.world = None
         self.name = name
         self._slot = None
@@ -179,7 +210,10 @@ class Robot:
         self._pose = cur
         self._pending = True
         if self.world is not None:
-            self.world._dirty = True
+            # a pose change is an upload of one row into the live engine, not a rebuild:
+            # velocities, stall flags and every other robot keep their state
+            self.world._pose_dirty = True
+            self.world._sensed = False
 
     def add_device(self, device):
         device.robot = self
@@ -197,17 +231,17 @@ class Robot:
         raise KeyError(item)
 
     def move(self, translate, rotate):
-        self._tvel[0] = translate * self.max_trans_velocity
-        self._tvel[2] = rotate * self.max_rotate_velocity
+        self._tvel[0] = _round_target(translate * self.max_trans_velocity)
+        self._tvel[2] = _round_target(rotate * self.max_rotate_velocity)
 
     def forward(self, translate):
-        self._tvel[0] = translate * self.max_trans_velocity
+        self._tvel[0] = _round_target(translate * self.max_trans_velocity)
 
     def backward(self, translate):
-        self._tvel[0] = -translate * self.max_trans_velocity
+        self._tvel[0] = _round_target(-translate * self.max_trans_velocity)
 
     def turn(self, rotate):
-        self._tvel[2] = rotate * self.max_rotate_velocity
+        self._tvel[2] = _round_target(rotate * self.max_rotate_velocity)
 
     def stop(self):
         self._tvel = [0.0, 0.0, 0.0]
@@ -234,6 +268,7 @@ class World:
         self._robots = []
         self._engine = None
         self._dirty = True
+        self._pose_dirty = False
         self._sensed = False
         self._state = {}
         self._obs = {}
@@ -313,9 +348,14 @@ class World:
 
     # -- engine plumbing -----------------------------------------------------------
     def _build(self):
+        """(Re)create the engine after a structural change (walls, bulbs, devices, robots).
+        The dynamic state of the robots that already existed -- actual velocities (the
+        ramp) and stall flags -- is carried over; only constructor / set_pose poses are new."""
         from .engine import BatchEngine
 
+        carry = None
         if self._engine is not None:
+            carry = (self._engine.download("vel"), self._engine.download("stalled"))
             self._engine.close()
         idx = {RangeSensor: 0, Camera: 0, LightSensor: 0, SmellSensor: 0}
         for r in self._robots:
@@ -323,11 +363,29 @@ class World:
                 d._index = idx[type(d)]
                 idx[type(d)] += 1
         self._engine = BatchEngine(self.to_scene(1), device=self.device)
+        if carry is not None:
+            n = min(carry[0].shape[1], len(self._robots))
+            vel = np.zeros((1, len(self._robots), 3), dtype=np.float64)
+            stalled = np.zeros((1, len(self._robots)), dtype=np.uint8)
+            vel[:, :n], stalled[:, :n] = carry[0][:, :n], carry[1][:, :n]
+            self._engine.upload("vel", vel)
+            self._engine.upload("stalled", stalled)
         for r in self._robots:
             r._pending = False
         self._dirty = False
+        self._pose_dirty = False
         self._sensed = False
         self._pull_state()
+
+    def _push_poses(self):
+        """Robot.set_pose on a live engine: upload the pose row, keep everything else."""
+        pose = np.array([[r.get_pose() for r in self._robots]], dtype=np.float64)
+        self._engine.upload("pose", pose)
+        for r in self._robots:
+            r._pending = False
+        self._pose_dirty = False
+        self._sensed = False
+        self._state["pose"] = pose
 
     def _pull_state(self):
         e = self._engine
@@ -341,6 +399,8 @@ class World:
     def _ensure_engine(self):
         if self._dirty or self._engine is None:
             self._build()
+        elif self._pose_dirty:
+            self._push_poses()
 
     def _ensure_sensed(self):
         self._ensure_engine()

@@ -164,6 +164,15 @@ int brs_download(brs_engine* e, int which, void* host, int first_world, int n_wo
  * see that round trip). */
 int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
 
+/* brs_step with the EXECUTED work counted on the device (for the roofline report; the step
+ * is a real one, state advances): *ray_tests = ray-segment tests the search loops ran (table
+ * entries that survived the range / cone culls x rays, plus direct-path segments x rays),
+ * *edge_tests = box-edge-vs-wall tests the collision classifier ran (4 per wall inside a
+ * robot's disc).  brs_count_tests() is the algorithmic count the culls are measured against.
+ * Synchronises `stream`. */
+int brs_step_counted(brs_engine* e, double time_step, unsigned flags, void* stream,
+                     unsigned long long* ray_tests, unsigned long long* edge_tests);
+
 /* Same step driven with HOST buffers (the end-to-end path): copies target
  * velocities host->device, steps, and copies every non-NULL observation back
  * device->host, all on `stream`.  h_* should be pinned. */
@@ -195,7 +204,8 @@ int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* worker
 /* Which of the two launch plans brs_create chose for this engine (for reports and tests):
  * *wide = 0: the fused kernel (one launch per step; Robot.step of tile n+1 overlaps the rays
  * of tile n inside a CTA), 1: the wide path (prep kernel + step kernel chained with
- * programmatic dependent launch; see csrc/brs_wide.cuh).  Both produce identical bits.
+ * programmatic dependent launch; see csrc/brs_wide.cuh), 2: the fused kernel fed by the prep
+ * kernel (its helper team skips the float64 pose proposal).  All produce identical bits.
  * *launches_per_step = kernels one brs_step enqueues. */
 int brs_path_info(brs_engine* e, int* wide, int* launches_per_step);
 

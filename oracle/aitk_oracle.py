@@ -64,6 +64,13 @@ class Switches:
     LIGHT_MULTIPLIER = 1000.0
     # U12: smell grid samples sum of gaussians at cell centres; walls ignored.
     SMELL_WALLS_BLOCK = False
+    # U3 / U9 / U11 -- facade constants that never reach the kernel (mirrored, under the same
+    # names, by aitk.robots_b200.world.FacadeDefaults; all UNVERIFIED recollection):
+    ROBOT_MAX_ROTATE_VELOCITY = math.pi / 4  # rad/s at rotate == 1
+    ROBOT_MAX_TRANS_VELOCITY = 2.0           # units per step at translate == 1
+    MOVE_ROUND_DIGITS = None                 # Robot.move rounds its targets to this many digits (None: no rounding)
+    CAMERA_DEFAULT_FOV = 60                  # degrees
+    CAMERA_DEFAULT_SIZE = (64, 32)
 
 
 SW = Switches
@@ -287,9 +294,9 @@ class Camera(_Device):
 
     def __init__(
         self,
-        width=64,
-        height=32,
-        a=60,
+        width=None,
+        height=None,
+        a=None,
         colorsFadeWithDistance=0.9,
         sizeFadeWithDistance=1.0,
         max_range=1000,
@@ -299,6 +306,9 @@ class Camera(_Device):
         self.robot = None
         self.name = name
         self._place(position)
+        width = SW.CAMERA_DEFAULT_SIZE[0] if width is None else width
+        height = SW.CAMERA_DEFAULT_SIZE[1] if height is None else height
+        a = SW.CAMERA_DEFAULT_FOV if a is None else a
         self.cameraShape = [width, height]
         self.angle = a * PI_OVER_180  # field of view
         self.colorsFadeWithDistance = colorsFadeWithDistance
@@ -442,10 +452,14 @@ class Robot:
         color="red",
         name="Robbie",
         height=0.25,
-        max_trans_velocity=2.0,
-        max_rotate_velocity=math.pi / 4,
+        max_trans_velocity=None,
+        max_rotate_velocity=None,
         bbox=None,
     ):
+        if max_trans_velocity is None:
+            max_trans_velocity = SW.ROBOT_MAX_TRANS_VELOCITY
+        if max_rotate_velocity is None:
+            max_rotate_velocity = SW.ROBOT_MAX_ROTATE_VELOCITY
         self.world = None
         self.name = name
         self.x, self.y = x, y
@@ -478,18 +492,22 @@ class Robot:
                 return device
         raise KeyError(item)
 
+    @staticmethod
+    def _target(v):
+        return v if SW.MOVE_ROUND_DIGITS is None else round(v, SW.MOVE_ROUND_DIGITS)
+
     def move(self, translate, rotate):
-        self.tvx = translate * self.max_trans_velocity
-        self.tva = rotate * self.max_rotate_velocity
+        self.tvx = self._target(translate * self.max_trans_velocity)
+        self.tva = self._target(rotate * self.max_rotate_velocity)
 
     def forward(self, translate):
-        self.tvx = translate * self.max_trans_velocity
+        self.tvx = self._target(translate * self.max_trans_velocity)
 
     def backward(self, translate):
-        self.tvx = -translate * self.max_trans_velocity
+        self.tvx = self._target(-translate * self.max_trans_velocity)
 
     def turn(self, rotate):
-        self.tva = rotate * self.max_rotate_velocity
+        self.tva = self._target(rotate * self.max_rotate_velocity)
 
     def stop(self):
         self.tvx = self.tvy = self.tva = 0.0
@@ -717,3 +735,9 @@ def assert_default_switches():
     assert SW.MOTION_DT_ON_VY_ONLY and SW.VELOCITY_RAMP and SW.STALL_ZEROES_VELOCITY
     assert SW.MOVE_ALL_THEN_SENSE and SW.RANGE_FAN_INCLUSIVE
     assert SW.LIGHT_MULTIPLIER == 1000.0 and not SW.SMELL_WALLS_BLOCK
+    # facade constants: the product's FacadeDefaults must carry the same values
+    from aitk_robots_b200.world import FacadeDefaults as FD
+
+    for k in ("ROBOT_MAX_ROTATE_VELOCITY", "ROBOT_MAX_TRANS_VELOCITY", "MOVE_ROUND_DIGITS", "CAMERA_DEFAULT_FOV",
+              "CAMERA_DEFAULT_SIZE"):
+        assert getattr(SW, k) == getattr(FD, k), k

@@ -38,19 +38,33 @@ def range_rays(world, dev):
     return rays
 
 
-def compare(scene, n_steps=1, worlds=None, camera=True):
+def compare(scene, n_steps=1, worlds=None, camera=True, ref_mod=None):
     """Step both engines n_steps and compare everything.  Returns a stats dict;
-    raises AssertionError on a parity violation."""
+    raises AssertionError on a parity violation.  `ref_mod`: the module that supplies the
+    reference observations -- the restatement oracle (default) or the real ``aitk.robots``
+    (tests/test_real_aitk.py); the geometric margins that excuse an end-point flip are
+    always measured on an oracle world stepped in lockstep."""
     orc.assert_default_switches()
     worlds = list(range(scene.n_worlds)) if worlds is None else list(worlds)
     gpu = run_engine(scene, n_steps)
+    return compare_outputs(scene, gpu, n_steps, worlds, camera, ref_mod)
+
+
+def compare_outputs(scene, gpu, n_steps, worlds, camera=True, ref_mod=None):
+    """`gpu`: dict of engine outputs after n_steps (run_engine layout), checked world by world."""
     stats = {"worlds": len(worlds), "ranges": 0, "range_hit_flips": 0, "max_rel_dist": 0.0, "pixels": 0,
              "pixel_mismatch": 0, "max_pose_err": 0.0, "lights": 0, "light_flips": 0}
     for i in worlds:
         world, devs = sa.build_world(scene, i)
         for _ in range(n_steps):
             world.step()
-        ref = sa.observe(world, devs, camera=camera)
+        if ref_mod is None or ref_mod is orc:
+            ref = sa.observe(world, devs, camera=camera)
+        else:
+            rworld, rdevs = sa.build_world(scene, i, ref_mod)
+            for _ in range(n_steps):
+                rworld.step()
+            ref = sa.observe(rworld, rdevs, camera=camera)
         size = max(world.width, world.height)
         # collision flags: exact
         assert list(gpu["stalled"][i]) == ref["stalled"], ("stalled", i, gpu["stalled"][i], ref["stalled"])

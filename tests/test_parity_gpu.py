@@ -133,6 +133,47 @@ def test_facade_dropin_api():
     assert robot.x > 100 and not robot.stalled
 
 
+def test_facade_set_pose_keeps_velocities_and_state():
+    """Robot.set_pose on a live world uploads one pose row: the velocity ramp of every robot
+    continues (upstream keeps vx / vy / va), and a structural change (add_wall) carries the
+    dynamic state into the rebuilt engine."""
+    from oracle import aitk_oracle as orc
+
+    def build(mod):
+        w = mod.World(300, 200)
+        r1, r2 = mod.Robot(60, 100, 0), mod.Robot(220, 100, 180)
+        r1.add_device(mod.RangeSensor(position=(8, 0), a=0, max=100, width=0))
+        w.add_robot(r1)
+        w.add_robot(r2)
+        r1.move(1.0, 0.3)
+        r2.move(0.5, -0.2)
+        return w, r1, r2
+
+    (gw, g1, g2), (ow, o1, o2) = build(rb), build(orc)
+    for _ in range(5):
+        gw.step()
+        ow.step()
+    # teleport robot 1 mid-ramp
+    g1.set_pose(100, 60, 90)
+    o1.x, o1.y, o1.a = 100.0, 60.0, 90 * orc.PI_OVER_180
+    o1.update_boundingbox(*o1.compute_boundingbox(o1.x, o1.y, o1.a))
+    assert g1.x == 100.0 and g1.y == 60.0
+    for _ in range(5):
+        gw.step()
+        ow.step()
+    for g, o in ((g1, o1), (g2, o2)):
+        assert abs(g.x - o.x) < 1e-9 and abs(g.y - o.y) < 1e-9 and abs(g.a - o.a) < 1e-9, (g.get_pose(), o.get_pose())
+    # structural change: the engine is rebuilt, velocities survive
+    gw.add_wall("blue", 10, 10, 20, 10, box=False)
+    ow.add_wall("blue", 10, 10, 20, 10, box=False)
+    for _ in range(5):
+        gw.step()
+        ow.step()
+    for g, o in ((g1, o1), (g2, o2)):
+        assert abs(g.x - o.x) < 1e-9 and abs(g.y - o.y) < 1e-9 and abs(g.a - o.a) < 1e-9, (g.get_pose(), o.get_pose())
+    assert g1[0].get_distance() == pytest.approx(o1[0].get_distance(), rel=1e-6)
+
+
 def test_zero_copy_tensor_and_bind_output():
     import torch
 
@@ -186,6 +227,7 @@ def test_culling_and_tiling_never_change_results(maker):
                 {"BRS_WIDE": "0", "BRS_NH": "2"}, {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "1"},
                 {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
                 {"BRS_WIDE": "0", "BRS_NR": "1", "BRS_GROUP_MIN": "1000"},
+                {"BRS_WIDE": "0", "BRS_PREP": "1"}, {"BRS_WIDE": "0", "BRS_PREP": "1", "BRS_TW": "3", "BRS_BIG": "1"},
                 {"BRS_WIDE": "1"}, {"BRS_WIDE": "1", "BRS_WNT": "32", "BRS_WTW": "1"},
                 {"BRS_WIDE": "1", "BRS_WNT": "32", "BRS_WTW": "3"}, {"BRS_WIDE": "1", "BRS_WNT": "96", "BRS_WTW": "2"},
                 {"BRS_WIDE": "1", "BRS_WNT": "256", "BRS_WTW": "5", "BRS_WBIG": "1"},

@@ -11,6 +11,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,nohe
 while IFS= read -r line; do
   [[ -z "$line" || "$line" == \#* ]] && continue
   kind=${line%% *}; rest=${line#* }
+  [ "$rest" = "$line" ] && rest=""
   if [ "$kind" = "pytest" ]; then
     timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 $rest > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/pytest_gpu.log
     continue
