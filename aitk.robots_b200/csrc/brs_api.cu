@@ -7,6 +7,7 @@
 #include "../../include/brs.h"
 #include "brs_kernels.cuh"
 #include "brs_wide.cuh"
+#include "brs_solo.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -71,6 +72,10 @@ struct brs_engine {
   bool w_big = false, pdl = true;
   bool prep_fused = false;  // fused kernel fed by brs_prep_kernel (two launches)
   const void* w_kfn = nullptr;
+  // the solo path (brs_solo.cuh): one warp per one-robot camera world, one launch
+  bool solo = false;
+  int sNT = 128, s_grid = 1, s_smem = 0, s_warps_per_sm = 0;
+  const void* s_kfn = nullptr;
 };
 
 static int pow2floor(int x) {
@@ -604,6 +609,48 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       }
     }
   }
+  // ---- the solo path: launch geometry ------------------------------------------
+  // One robot carrying one camera of 32 / 64 / 128 columns and nothing else, flat sky and
+  // ground: a warp per world (brs_solo.cuh).  Needs enough worlds to give every resident warp
+  // a few; smaller batches keep the fused kernel, which splits one world over a CTA.
+  {
+    const int w = e->cam_w, nr = w / 32;
+    const bool shape_ok = R == 1 && cfg->n_camera == 1 && cfg->n_range == 0 && cfg->n_light == 0 && cfg->n_smell == 0 &&
+                          e->n_group == 1 && w % 32 == 0 && (nr == 1 || nr == 2 || nr == 4) && e->cam_h <= 16384 &&
+                          cfg->seg_cap <= 1024;
+    if (shape_ok) {
+      const SoloLayout SL = make_solo_layout(cfg->seg_cap);
+      const int variant = env_int("BRS_SOLO_CTAS", 6);  // resident 128-thread CTAs per SM the register cap is set for
+      const void* sk = nullptr;
+#define BRS_SK(CT) (nr == 1 ? (const void*)brs_solo_kernel<1, 128, CT> : nr == 2 ? (const void*)brs_solo_kernel<2, 128, CT> : (const void*)brs_solo_kernel<4, 128, CT>)
+      if (variant >= 8) sk = BRS_SK(8);
+      else if (variant == 7) sk = BRS_SK(7);
+      else if (variant == 5) sk = BRS_SK(5);
+      else if (variant <= 4) sk = BRS_SK(4);
+      else sk = BRS_SK(6);
+#undef BRS_SK
+      e->sNT = 128;
+      e->s_smem = SL.per_warp * (e->sNT / 32);
+      e->s_kfn = sk;
+      bool ok = (size_t)e->s_smem <= prop.sharedMemPerBlockOptin;
+      int snb = 0;
+      if (ok) {
+        ce = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, e->s_smem);
+        if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&snb, sk, e->sNT, e->s_smem);
+        ok = ce == cudaSuccess && snb >= 1;
+        if (!ok) cudaGetLastError();
+      }
+      if (ok) {
+        snb = std::min(snb, env_int("BRS_SOLO_MAX_CTAS", 32));
+        e->s_warps_per_sm = snb * (e->sNT / 32);
+        const int want = (cfg->n_worlds + (e->sNT / 32) - 1) / (e->sNT / 32);  // at least one world per warp
+        e->s_grid = std::max(1, std::min(want, snb * e->sm_count));
+        const bool auto_solo = cfg->n_worlds >= env_int("BRS_SOLO_MIN_WORLDS", 4 * e->s_warps_per_sm * e->sm_count);
+        e->solo = env_int("BRS_SOLO", auto_solo ? 1 : 0) != 0;
+        if (e->solo) { e->wide = false; e->prep_fused = false; }
+      }
+    }
+  }
   *out = e;
   return BRS_OK;
 }
@@ -765,7 +812,9 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   KParams p;
   fill_params(e, p, time_step, flags, e->wide);
   void* args[] = {(void*)&p};
-  if (!e->wide && !e->prep_fused) {
+  if (e->solo) {
+    CK(cudaLaunchKernel(e->s_kfn, dim3(e->s_grid), dim3(e->sNT), args, (size_t)e->s_smem, (cudaStream_t)stream));
+  } else if (!e->wide && !e->prep_fused) {
     CK(cudaLaunchKernel(e->kfn, dim3(e->grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
   } else {
     // prep (thread per robot half), then the step kernel under programmatic dependent launch:
@@ -853,27 +902,27 @@ extern "C" int brs_count_tests(brs_engine* e, unsigned flags, void* stream, unsi
 
 extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem_bytes, int* sm_count) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_launch_info: null engine");
-  if (threads) *threads = e->wide ? e->wNT : e->T;
-  if (ctas) *ctas = e->wide ? e->w_grid : e->grid;
-  if (smem_bytes) *smem_bytes = e->wide ? e->w_smem : e->smem;
+  if (threads) *threads = e->solo ? e->sNT : e->wide ? e->wNT : e->T;
+  if (ctas) *ctas = e->solo ? e->s_grid : e->wide ? e->w_grid : e->grid;
+  if (smem_bytes) *smem_bytes = e->solo ? e->s_smem : e->wide ? e->w_smem : e->smem;
   if (sm_count) *sm_count = e->sm_count;
   return BRS_OK;
 }
 
 extern "C" int brs_path_info(brs_engine* e, int* wide, int* launches_per_step) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_path_info: null engine");
-  if (wide) *wide = e->wide ? 1 : (e->prep_fused ? 2 : 0);
-  if (launches_per_step) *launches_per_step = (e->wide || e->prep_fused) ? 2 : 1;
+  if (wide) *wide = e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
+  if (launches_per_step) *launches_per_step = (!e->solo && (e->wide || e->prep_fused)) ? 2 : 1;
   return BRS_OK;
 }
 
 extern "C" int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* workers, int* cols_per_thread,
                              int* n_groups) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_tile_info: null engine");
-  if (worlds_per_tile) *worlds_per_tile = e->wide ? e->wTW : e->TW;
-  if (n_tiles) *n_tiles = e->wide ? e->w_tiles : e->n_tiles;
-  if (workers) *workers = e->wide ? e->wNT : e->NW;
-  if (cols_per_thread) *cols_per_thread = e->NR;
+  if (worlds_per_tile) *worlds_per_tile = e->solo ? 1 : e->wide ? e->wTW : e->TW;
+  if (n_tiles) *n_tiles = e->solo ? e->cfg.n_worlds : e->wide ? e->w_tiles : e->n_tiles;
+  if (workers) *workers = e->solo ? e->sNT : e->wide ? e->wNT : e->NW;
+  if (cols_per_thread) *cols_per_thread = e->solo ? e->cam_w / 32 : e->NR;
   if (n_groups) *n_groups = e->n_group;
   return BRS_OK;
 }

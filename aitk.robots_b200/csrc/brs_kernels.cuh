@@ -685,10 +685,10 @@ __device__ __forceinline__ void team_sync(int id, int nthreads) {
 #define BRS_CQ_MAX 252
 // FP32 classification of ONE box edge (ax,ay)->(bx2,by2) of a proposal against wall s =
 // (x1, y1, ex, ey), widened by an explicit error bound: false = certain miss.
-__device__ __forceinline__ bool edge_maybe_hits(const KParams& p, const double* __restrict__ pr, int r, const float4 s,
-                                                double ax, double ay, double bx2, double by2) {
-  const float cx = (float)pr[8], cy = (float)pr[9];
-  const float rad = (float)p.robots[r].radius + p.cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
+// (cx, cy: the proposed centre in FP32; radius: the box circumradius)
+__device__ __forceinline__ bool edge_maybe_hits_at(float cx, float cy, float radius, float cull_margin, const float4 s,
+                                                   double ax, double ay, double bx2, double by2) {
+  const float rad = radius + cull_margin + 1e-5f * (fabsf(cx) + fabsf(cy));
   const float cscale = 4e-7f * (fabsf(cx) + fabsf(cy) + rad + 1.f);
   const float pcx = (float)ax, pcy = (float)ay;
   const float pex = (float)(bx2 - ax), pey = (float)(by2 - ay);
@@ -701,6 +701,10 @@ __device__ __forceinline__ bool edge_maybe_hits(const KParams& p, const double* 
   const float tol = cscale * (fabsf(s.z) + fabsf(s.w) + fabsf(pex) + fabsf(pey)) + 1e-5f * (fabsf(na) + fabsf(nb) + ad);
   const float sa_ = den < 0.f ? -na : na, sb_ = den < 0.f ? -nb : nb;
   return !(sa_ < -tol || sa_ > ad + tol || sb_ < -tol || sb_ > ad + tol);
+}
+__device__ __forceinline__ bool edge_maybe_hits(const KParams& p, const double* __restrict__ pr, int r, const float4 s,
+                                                double ax, double ay, double bx2, double by2) {
+  return edge_maybe_hits_at((float)pr[8], (float)pr[9], (float)p.robots[r].radius, p.cull_margin, s, ax, ay, bx2, by2);
 }
 __device__ __forceinline__ bool box_hits_wall(const KParams& p, const double* __restrict__ wsb,
                                               const uint32_t* __restrict__ rawb, const float4* __restrict__ st, int i,

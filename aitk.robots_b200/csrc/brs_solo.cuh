@@ -1,0 +1,394 @@
+// brs_solo.cuh -- the SOLO path of World.step: one WARP owns a world from its wall store to
+// its finished picture, for the largest class of batched worlds -- one robot carrying one
+// camera (BASELINE.json config 4: a million such worlds).
+//
+// Why a third launch plan.  The fused kernel (brs_kernels.cuh) and the wide path
+// (brs_wide.cuh) run every world shape through the same tile machinery: runtime robot /
+// group / sensor counts, fast divisions to find (world, robot, task) from a flat index, a
+// candidate queue with atomics, a list-order replay over bit masks, column records in shared
+// memory, team barriers between phases.  For a one-robot camera world most of that is
+// overhead: ncu counted 2,370 warp-instructions per world of which the FP32 search is 400.
+// Here everything that the shape makes constant is a compile-time constant, a phase hands
+// its results to the next one in registers (shuffles), and nothing ever waits for another
+// warp:
+//
+//   PREP     two lanes per world, BRS_SOLO_BATCH worlds at a time: the float64 pose proposal
+//            of Robot.step (velocity ramp, sincos) with every lane busy;
+//   then per world, all 32 lanes:
+//   TMA      the world's wall store (SoA, 20*cap bytes) by one bulk copy into the warp's own
+//            buffer, requested while the previous picture is being written;
+//   COLLIDE  FP32 disc cull over the walls (lane per wall), FP32 edge classifier and exact
+//            float64 4-edge test on what falls inside (rare: warp-uniform branch);
+//   TABLE    shared-origin table m, q per wall, range / cone cull, ballot compaction;
+//   SENSE    NR adjacent columns per lane: FP32 nearest-hit search over the compacted table
+//            (broadcast LDS.128), float64 refinement of the winner, column record in registers;
+//   PAINT    lane -> (row slot, 4-column quad), records fetched by shuffles; rows above every
+//            wall top / inside every wall / below every bottom of the quad are constant
+//            16-byte stores, only the rows in between take per-pixel selects; a warp store
+//            covers 512 contiguous bytes;
+//   COMMIT   per batch: poses, velocities, stalled flags to HBM.
+//
+// Same device functions and operation order as the other two paths: the outputs are
+// bit-identical (tests/test_parity_gpu.py::test_culling_and_tiling_never_change_results).
+#pragma once
+#include "brs_kernels.cuh"
+
+namespace brs {
+
+#define BRS_SOLO_BATCH 16  // worlds per PREP pass of a warp (two lanes per world)
+#define BRS_SOLO_REC 16    // doubles per world record
+// record (doubles): committed x y a cos sin | proposed x y a cos sin vx vy va | int2 (S, bits of
+// the world extent) | float4 collision disc (2 doubles)
+#define BRS_SR_POSE 0
+#define BRS_SR_PROP 5
+#define BRS_SR_META 13
+#define BRS_SR_CPAR 14
+
+struct SoloLayout {
+  int raw, tab, idx, rec, mbar, per_warp;
+};
+__host__ __device__ inline SoloLayout make_solo_layout(int seg_cap) {
+  SoloLayout L;
+  int o = 0;
+  L.raw = o; o += align_up(5 * seg_cap * 4, 16);
+  L.tab = o; o += seg_cap * 16;
+  L.idx = o; o += align_up(seg_cap * 2, 16);
+  L.rec = o; o += BRS_SOLO_BATCH * BRS_SOLO_REC * 8;
+  L.mbar = o; o += 16;
+  L.per_warp = align_up(o, 128);
+  return L;
+}
+
+#ifdef __CUDACC__
+
+// One half of Robot.step's proposal for the solo record: the same operations, in the same
+// order, as prep_robot_half (brs_kernels.cuh) minus the box corners (a lone robot's box is
+// only needed when a wall falls inside its disc; collide() rebuilds it there).
+__device__ __forceinline__ void solo_prep_half(const KParams& p, const RobotDev& rd, int w, bool prop,
+                                               double* __restrict__ r) {
+  const size_t o = (size_t)w * 3;
+  const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
+  const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
+  double vx = v0, vy = v1, va = v2, pa = a;
+  if (prop) {
+    const double* tv = p.tvel + o;
+    vx = deltav(tv[0], v0, rd.vx_ramp, p.dt);
+    vy = deltav(tv[1], v1, rd.vy_ramp, p.dt);
+    va = deltav(tv[2], v2, rd.va_ramp, p.dt);
+    pa = ds(a, dm(va, p.dt));
+  }
+  double sn, cs;
+  sincos(prop ? da(-pa, BRS_PI_OVER_2) : a, &sn, &cs);
+  const double c = prop ? sn : cs, sgn = prop ? cs : sn;
+  if (prop) {
+    const double px = da(x, da(dm(vx, sn), dm(dm(vy, cs), p.dt)));
+    const double py = da(y, ds(dm(vx, cs), dm(dm(vy, sn), p.dt)));
+    r[BRS_SR_PROP] = px; r[BRS_SR_PROP + 1] = py; r[BRS_SR_PROP + 2] = pa;
+    r[BRS_SR_PROP + 3] = c; r[BRS_SR_PROP + 4] = sgn;
+    r[BRS_SR_PROP + 5] = vx; r[BRS_SR_PROP + 6] = vy; r[BRS_SR_PROP + 7] = va;
+    const float cxf = (float)px, cyf = (float)py;
+    const float rad = (float)rd.radius + p.cull_margin + 1e-5f * (fabsf(cxf) + fabsf(cyf));
+    *(float4*)(r + BRS_SR_CPAR) = make_float4(cxf, cyf, rad * rad, 0.f);
+  } else {
+    r[BRS_SR_POSE] = x; r[BRS_SR_POSE + 1] = y; r[BRS_SR_POSE + 2] = a;
+    r[BRS_SR_POSE + 3] = c; r[BRS_SR_POSE + 4] = sgn;
+    const int S = min(max(p.seg_count[w], 0), p.seg_cap);
+    const float ext = fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]);
+    *(int2*)(r + BRS_SR_META) = make_int2(S, __float_as_int(ext));
+  }
+}
+
+// wall j of the warp's staged store as the FP32 search segment (x1, y1, ex, ey)
+__device__ __forceinline__ float4 solo_wall(const uint32_t* __restrict__ raw, int SC, int j) {
+  const float ax = __uint_as_float(raw[j]), ay = __uint_as_float(raw[SC + j]);
+  return make_float4(ax, ay, __uint_as_float(raw[2 * SC + j]) - ax, __uint_as_float(raw[3 * SC + j]) - ay);
+}
+
+// Robot-vs-wall collision of the proposal (collide_commit_tile's COLLIDE for one robot):
+// warp-uniform result.
+__device__ __forceinline__ bool solo_collide(const KParams& p, const RobotDev& rd, const double* __restrict__ r,
+                                             const uint32_t* __restrict__ raw, int SC, int S, int lane) {
+  const float4 cp = *(const float4*)(r + BRS_SR_CPAR);
+  bool have_box = false;
+  double ax = 0, ay = 0, bx2 = 0, by2 = 0;
+  unsigned long long n_cls = 0;
+  bool hit = false;
+  for (int j0 = 0; j0 < S; j0 += 32) {
+    const int j = j0 + lane;
+    bool inside = false;
+    if (j < S) {
+      const float4 s = solo_wall(raw, SC, j);
+      const float dx = cp.x - s.x, dy = cp.y - s.y;
+      const float ee = fmaf(s.z, s.z, s.w * s.w);
+      float h = fmaf(dx, s.z, dy * s.w) * rcp_approx(ee);
+      h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
+      const float vx = fmaf(-h, s.z, dx), vy = fmaf(-h, s.w, dy);
+      inside = fmaf(vx, vx, vy * vy) <= cp.z;
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, inside);
+    while (bal) {  // rare, warp-uniform: lanes 4k+e test box edge e (all octets redundantly)
+      const int jj = j0 + __ffs(bal) - 1;
+      bal &= bal - 1;
+      if (!have_box) {
+        have_box = true;
+        const int e = lane & 3, e2 = (e + 1) & 3;
+        const double px = r[BRS_SR_PROP], py = r[BRS_SR_PROP + 1], c = r[BRS_SR_PROP + 3], sgn = r[BRS_SR_PROP + 4];
+        ax = da(px, ds(dm(c, rd.cox[e]), dm(sgn, rd.coy[e])));
+        ay = da(py, da(dm(sgn, rd.cox[e]), dm(c, rd.coy[e])));
+        bx2 = da(px, ds(dm(c, rd.cox[e2]), dm(sgn, rd.coy[e2])));
+        by2 = da(py, da(dm(sgn, rd.cox[e2]), dm(c, rd.coy[e2])));
+      }
+      const float4 sj = solo_wall(raw, SC, jj);
+      const bool maybe = edge_maybe_hits_at((float)r[BRS_SR_PROP], (float)r[BRS_SR_PROP + 1], (float)rd.radius,
+                                            p.cull_margin, sj, ax, ay, bx2, by2);
+      n_cls += 4;
+      if (__ballot_sync(0xffffffffu, maybe)) {
+        const double x3 = (double)__uint_as_float(raw[jj]), y3 = (double)__uint_as_float(raw[SC + jj]);
+        const double x4 = (double)__uint_as_float(raw[2 * SC + jj]), y4 = (double)__uint_as_float(raw[3 * SC + jj]);
+        const bool h = isect64_bool(ax, ay, ds(bx2, ax), ds(by2, ay), x3, y3, x4, y4);
+        if (__ballot_sync(0xffffffffu, h)) hit = true;
+      }
+      if (hit) break;
+    }
+    if (hit) break;
+  }
+  if (p.counters && lane == 0 && n_cls) atomicAdd(&p.counters[1], n_cls);
+  return hit;
+}
+
+// PAINT of one picture by one warp.  Lane -> (row slot, quad): a row of W = 32*NR pixels is
+// Q = 8*NR quads, 32 / Q rows per warp store, every store covers 512 contiguous bytes.
+// rec_rgba / rec_tb: this lane's NR column records (tb = top | bot << 16; a column that hit
+// nothing is a "wall" of colour 0 over every row, which is what the blank picture holds).
+template <int NR>
+__device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32_t (&rec_rgba)[NR],
+                                           const uint32_t (&rec_tb)[NR], const uint32_t* __restrict__ rowsky,
+                                           const uint32_t* __restrict__ rowgnd, bool flat, int lane, int H) {
+  constexpr int Q = 8 * NR, RP = 32 / Q;
+  const int q = lane % Q, r0 = lane / Q;
+  uint32_t rgba[4];
+  int top[4], bot[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // column 4q + k lives in lane (4q + k) / NR, slot (4q + k) % NR == k % NR
+    const int src = (4 * q + k) / NR;
+    const uint32_t a = __shfl_sync(0xffffffffu, rec_rgba[k % NR], src);
+    const uint32_t b = __shfl_sync(0xffffffffu, rec_tb[k % NR], src);
+    rgba[k] = a;
+    top[k] = (int)(b & 0xffffu);
+    bot[k] = (int)(b >> 16);
+  }
+  uint4* o = out + (size_t)r0 * Q + q;
+  if (flat) {
+    const uint32_t sky = rowsky[0], gnd = rowgnd[0];
+    const int t0 = min(min(top[0], top[1]), min(top[2], top[3]));
+    const int t1 = max(max(top[0], top[1]), max(top[2], top[3]));
+    const int b0 = min(min(bot[0], bot[1]), min(bot[2], bot[3]));
+    const int b1 = max(max(max(bot[0], bot[1]), max(bot[2], bot[3])), t1);
+    const int e1 = min(t0, H), e2 = min(t1, H), e3 = min(b0, H), e4 = min(b1, H);
+    const uint4 skyq = make_uint4(sky, sky, sky, sky), gndq = make_uint4(gnd, gnd, gnd, gnd);
+    const uint4 wallq = make_uint4(rgba[0], rgba[1], rgba[2], rgba[3]);
+    int j = r0;
+#define BRS_SOLO_PX(k) (j < top[k] ? sky : (j < bot[k] ? rgba[k] : gnd))
+#pragma unroll 1
+    for (; j < e1; j += RP, o += 32) __stcs(o, skyq);
+#pragma unroll 1
+    for (; j < e2; j += RP, o += 32) __stcs(o, make_uint4(BRS_SOLO_PX(0), BRS_SOLO_PX(1), BRS_SOLO_PX(2), BRS_SOLO_PX(3)));
+#pragma unroll 1
+    for (; j < e3; j += RP, o += 32) __stcs(o, wallq);
+#pragma unroll 1
+    for (; j < e4; j += RP, o += 32) __stcs(o, make_uint4(BRS_SOLO_PX(0), BRS_SOLO_PX(1), BRS_SOLO_PX(2), BRS_SOLO_PX(3)));
+#pragma unroll 1
+    for (; j < H; j += RP, o += 32) __stcs(o, gndq);
+#undef BRS_SOLO_PX
+  } else {
+#pragma unroll 1
+    for (int j = r0; j < H; j += RP, o += 32) {
+      const uint32_t sky = rowsky[j], gnd = rowgnd[j];
+      uint32_t px[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) px[k] = j < top[k] ? sky : (j < bot[k] ? rgba[k] : gnd);
+      __stcs(o, make_uint4(px[0], px[1], px[2], px[3]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// The solo step kernel.  NR = camera columns per lane (camera width = 32 * NR); NT threads per
+// CTA (independent warps: the CTA is only the unit of shared-memory allocation).
+// Worlds are dealt to the warps as contiguous, equal ranges: every warp finishes at about the
+// same time without a scheduler.
+// ------------------------------------------------------------------------------
+template <int NR, int NT, int MIN_CTAS>
+__global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int SC = p.seg_cap;
+  const SoloLayout L = make_solo_layout(SC);
+  unsigned char* const sm = smem + (size_t)wib * L.per_warp;
+  const uint32_t* const raw = (const uint32_t*)(sm + L.raw);
+  float4* const tab = (float4*)(sm + L.tab);
+  uint16_t* const ix = (uint16_t*)(sm + L.idx);
+  double* const rec = (double*)(sm + L.rec);
+  const uint32_t bar = smem_u32(sm + L.mbar);
+  const bool do_move = p.flags & 1u, do_cam = (p.flags & 4u) && p.n_camera > 0;
+  if (!do_move && !do_cam) return;
+
+  const unsigned nwarps = gridDim.x * (NT / 32), gw = blockIdx.x * (NT / 32) + wib;
+  const int wbeg = (int)((unsigned long long)p.n_worlds * gw / nwarps);
+  const int wend = (int)((unsigned long long)p.n_worlds * (gw + 1) / nwarps);
+  if (wbeg >= wend) return;
+
+  const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, world_bytes);
+    tma_bulk_g2s(smem_u32(raw), p.seg + (size_t)wbeg * 5 * SC, world_bytes, bar);
+  }
+  __syncwarp();
+
+  const RobotDev& rd = p.robots[0];
+  const CameraDev& cd = p.cameras[0];
+  const GroupDev& gd = p.groups[0];
+  const int H = p.cam_h;
+  const double Hd = (double)cd.height;
+  double2 ccs[NR];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) ccs[k] = do_cam ? p.cam_cs[lane * NR + k] : make_double2(0.0, 0.0);
+  uint32_t parity = 0;
+
+  for (int b0 = wbeg; b0 < wend; b0 += BRS_SOLO_BATCH) {
+    const int nb = min(BRS_SOLO_BATCH, wend - b0);
+    // ---------------- PREP ----------------------------------------------------------------
+    {
+      const int wl = lane >> 1;
+      const bool prop = lane & 1;
+      if (wl < nb && (!prop || do_move)) solo_prep_half(p, rd, b0 + wl, prop, rec + wl * BRS_SOLO_REC);
+    }
+    __syncwarp();
+    unsigned stall_mask = 0;
+    for (int k = 0; k < nb; ++k) {
+      const int w = b0 + k;
+      const double* r = rec + k * BRS_SOLO_REC;
+      const int2 meta = *(const int2*)(r + BRS_SR_META);
+      const int S = meta.x;
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      // ---------------- COLLIDE ------------------------------------------------------------
+      bool hit = true;  // !do_move: the committed state stays
+      if (do_move) hit = solo_collide(p, rd, r, raw, SC, S, lane);
+      if (hit) stall_mask |= 1u << k;
+      uint32_t rec_rgba[NR], rec_tb[NR];
+      if (do_cam) {
+        // final state of the robot: the proposal if it moves, the committed state otherwise
+        const double* f = hit ? r + BRS_SR_POSE : r + BRS_SR_PROP;
+        const double fx = f[0], fy = f[1], fc = f[3], fs = f[4];
+        // ---------------- TABLE -------------------------------------------------------------
+        // (the group's origin and cone in the world frame: COMMIT of the other paths)
+        const double ox = da(fx, ds(dm(fc, gd.mx), dm(fs, gd.my)));
+        const double oy = da(fy, da(dm(fs, gd.mx), dm(fc, gd.my)));
+        GroupCull gc;
+        {
+          const float cf = (float)fc, sf = (float)fs;
+          gc.lo_x = cf * gd.lo_c - sf * gd.lo_s; gc.lo_y = sf * gd.lo_c + cf * gd.lo_s;
+          gc.hi_x = cf * gd.hi_c - sf * gd.hi_s; gc.hi_y = sf * gd.hi_c + cf * gd.hi_s;
+          gc.ax_x = cf * gd.ax_c - sf * gd.ax_s; gc.ax_y = sf * gd.ax_c + cf * gd.ax_s;
+          gc.range2 = gd.range * gd.range;
+          gc.has_cone = gd.has_cone;
+          gc.ox = (float)ox;
+          gc.oy = (float)oy;
+        }
+        int cw = 0;
+        for (int j0 = 0; j0 < S; j0 += 32) {
+          const int j = j0 + lane;
+          float4 t;
+          bool keep = false;
+          if (j < S) keep = table_entry(solo_wall(raw, SC, j), gc, t);
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const int pos = cw + __popc(bal & ((1u << lane) - 1u));
+            tab[pos] = t;
+            ix[pos] = (uint16_t)j;
+          }
+          cw += __popc(bal);
+        }
+        __syncwarp();
+        if (p.counters && lane == 0) atomicAdd(&p.counters[0], (unsigned long long)cw * (unsigned)p.cam_w);
+        // ---------------- SENSE -------------------------------------------------------------
+        double x2[NR], y2[NR];
+        float rx[NR], ry[NR];
+        uint32_t key[NR];
+        int idx[NR];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+          const double dxu = ds(dm(fc, ccs[c].x), dm(fs, ccs[c].y));  // cos(a + theta_i)
+          const double dyu = da(dm(fs, ccs[c].x), dm(fc, ccs[c].y));  // sin(a + theta_i)
+          x2[c] = da(dm(dxu, cd.max_range), ox);
+          y2[c] = da(dm(dyu, cd.max_range), oy);
+          rx[c] = (float)ds(x2[c], ox);
+          ry[c] = (float)ds(y2[c], oy);
+          key[c] = BRS_GKEY_INIT;
+          idx[c] = -1;
+        }
+        search_group<NR, true>(tab, 0, cw, 0, 1, rx, ry, key, idx);
+        const double wsize = (double)__int_as_float(meta.y);
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+          // Camera._update of one column (camera_column without other robots)
+          rec_rgba[c] = 0u;
+          rec_tb[c] = 0x7fff0000u;  // nothing hit: colour 0 over every row
+          if (idx[c] >= 0) {
+            const int j = ix[idx[c]];
+            const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
+            const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
+            const double dist = dm(ua64(ox, oy, x2[c], y2[c], x3, y3, x4, y4), cd.max_range);
+            const double dw = dist / wsize;
+            const double s = clamp01(ds(1.0, dm(dw, cd.size_fade)));
+            const double sc = clamp01(ds(1.0, dm(dw, cd.color_fade)));
+            rec_rgba[c] = shade(raw[4 * SC + j], sc);
+            const double high = dm(ds(1.0, s), Hd);
+            const int top = (int)ceil(high / 2.0), bot = (int)ceil(ds(Hd, high / 2.0));
+            rec_tb[c] = (uint32_t)min(max(top, 0), 0x7fff) | ((uint32_t)min(max(bot, 0), 0x7fff) << 16);
+          }
+        }
+      }
+      // every lane is done with this world's walls: request the next world's while the
+      // picture is written
+      __syncwarp();
+      if (lane == 0 && w + 1 < wend) {
+        mbar_expect_tx(bar, world_bytes);
+        tma_bulk_g2s(smem_u32(raw), p.seg + (size_t)(w + 1) * 5 * SC, world_bytes, bar);
+      }
+      // ---------------- PAINT -----------------------------------------------------------------
+      if (do_cam)
+        solo_paint<NR>((uint4*)(p.cam_out + (size_t)w * (size_t)H * p.cam_w * 4), rec_rgba, rec_tb, p.row_sky, p.row_gnd,
+                       p.flat_rows != 0, lane, H);
+    }
+    // ---------------- COMMIT ------------------------------------------------------------------
+    if (do_move) {
+      const int wl = lane >> 1;
+      if (wl < nb) {
+        const bool hit = (stall_mask >> wl) & 1u;
+        const double* r = rec + wl * BRS_SOLO_REC;
+        const size_t o = (size_t)(b0 + wl) * 3;
+        if (lane & 1) {
+          p.vel[o] = hit ? 0.0 : r[BRS_SR_PROP + 5];
+          p.vel[o + 1] = hit ? 0.0 : r[BRS_SR_PROP + 6];
+          p.vel[o + 2] = hit ? 0.0 : r[BRS_SR_PROP + 7];
+        } else {
+          if (!hit) {
+            p.pose[o] = r[BRS_SR_PROP];
+            p.pose[o + 1] = r[BRS_SR_PROP + 1];
+            p.pose[o + 2] = r[BRS_SR_PROP + 2];
+          }
+          p.stalled[b0 + wl] = (uint8_t)(hit ? 1 : 0);
+        }
+      }
+    }
+    __syncwarp();  // the records are overwritten by the next batch
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace brs

@@ -128,51 +128,47 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------ CPU legs
+def _ref_module(use_real):
+    """The module that supplies World / Robot / devices on the CPU legs: the real
+    ``aitk.robots`` when it is importable (also from baseline/_ref) and asked for, else the
+    in-repo float64 restatement (oracle/)."""
+    from oracle import aitk_oracle as orc
+    from oracle import scene_adapter as sa
+
+    if use_real:
+        mod = sa.find_real_aitk(ROOT)
+        if mod is not None:
+            return mod, "aitk"
+    return orc, "port"
+
+
 def _cpu_worker(args):
-    """Steps `count` worlds of the scene slice once through the pure-Python oracle
-    (World.step + every Camera.take_picture); returns (world_steps, tests, seconds)."""
-    config, first, count, n_steps = args
+    """Steps `count` worlds of the scene slice `n_steps` times on the CPU (World.step + every
+    Camera.take_picture); returns (world_steps, tests, seconds)."""
+    config, first, count, n_steps, use_real = args
     import aitk_robots_b200 as rb
     from oracle import scene_adapter as sa
 
+    mod, kind = _ref_module(use_real)
     scene = make_scene(rb, config, count, first)
     t0 = time.perf_counter()
     tests = 0
     for i in range(count):
-        world, devs = sa.build_world(scene, i)
-        world.counted_tests = 0
+        world, devs = sa.build_world(scene, i, mod)
+        if kind == "port":
+            world.counted_tests = 0
         for _ in range(n_steps):
             world.step()
             for cam in devs["camera"]:
                 cam.take_picture()
-        tests += world.counted_tests
+        tests += world.counted_tests if kind == "port" else scene.slice(i, 1).tests_per_step() * n_steps
     return count * n_steps, tests, time.perf_counter() - t0
-
-
-def _real_aitk():
-    """The real reference engine, if the driver installed one (baseline/_ref)."""
-    try:
-        import aitk.robots  # noqa: F401
-
-        return True
-    except Exception:
-        pass
-    ref = os.path.join(ROOT, "baseline", "_ref")
-    if os.path.isdir(ref):
-        sys.path.insert(0, ref)
-        try:
-            import aitk.robots  # noqa: F401
-
-            return True
-        except Exception:
-            sys.path.remove(ref)
-    return False
 
 
 _POOL = None
 
 
-def _pool(cores):
+def _pool(cores, use_real):
     global _POOL
     if _POOL is None:
         import multiprocessing as mp
@@ -181,48 +177,57 @@ def _pool(cores):
 
         _POOL = mp.get_context("spawn").Pool(cores)
         atexit.register(lambda: (_POOL.close(), _POOL.join()))
-        _POOL.map(_cpu_worker, [("config1", 0, 1, 1)] * cores)  # imports done before anything is timed
+        _POOL.map(_cpu_worker, [("config1", 0, 1, 1, use_real)] * cores)  # imports done before anything is timed
     return _POOL
 
 
-def cpu_throughput(config, target_seconds, cores=None, first_world=10_000_000):
-    """Oracle ("port") throughput over all host cores on a bounded sample of the workload."""
+def cpu_throughput(config, target_seconds, cores=None, first_world=10_000_000, use_real=True):
+    """Reference-CPU throughput over all host cores on a bounded sample of the workload."""
     cores = cores or os.cpu_count() or 1
+    _, kind = _ref_module(use_real)
     # calibrate on one world-step
-    ws, tests, dt = _cpu_worker((config, first_world, 1, 1))
+    ws, tests, dt = _cpu_worker((config, first_world, 1, 1, use_real))
     per_world = max(dt, 1e-4)
     n_per_core = max(1, int(target_seconds / per_world))
-    jobs = [(config, first_world + 1 + c * n_per_core, n_per_core, 1) for c in range(cores)]
-    pool = _pool(cores)
+    jobs = [(config, first_world + 1 + c * n_per_core, n_per_core, 1, use_real) for c in range(cores)]
+    pool = _pool(cores, use_real)
     t0 = time.perf_counter()
     res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
     # workers import + build scenes inside their own timers: use the slowest worker's compute time
     busy = max(r[2] for r in res)
     wsteps, tests = sum(r[0] for r in res), sum(r[1] for r in res)
-    return {"world_steps_per_sec": wsteps / busy, "tests_per_sec": tests / busy, "cores": cores,
-            "sample": "%d worlds x 1 World.step (+take_picture) of %s, %d per core, pure-Python float64 port"
-                      % (wsteps, config, n_per_core), "wall_s": wall, "busy_s": busy}
+    what = "the real aitk.robots package" if kind == "aitk" else "pure-Python float64 port (oracle/)"
+    return {"world_steps_per_sec": wsteps / busy, "tests_per_sec": tests / busy, "cores": cores, "kind": kind,
+            "sample": "%d worlds x 1 World.step (+take_picture) of %s, %d per core, %s"
+                      % (wsteps, config, n_per_core, what), "wall_s": wall, "busy_s": busy}
+
+
+def config1_as_written(use_real=True, n_steps=1000):
+    """BASELINE.json configs[0] exactly as written: ONE 200x150 world, 1 robot with 1
+    RangeSensor (max 100), 4 walls, 1000 World.steps, a single CPU process, noise off."""
+    ws, tests, dt = _cpu_worker(("config1", 0, 1, n_steps, use_real))
+    _, kind = _ref_module(use_real)
+    return {"world_steps_per_sec": ws / dt, "seconds_for_1000_steps": dt * 1000.0 / n_steps, "steps": n_steps,
+            "tests_per_sec": tests / dt, "cores": 1, "kind": kind}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  The real
-    aitk.robots cannot be installed here: the in-repo port stands in."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host
+    cores -- the real aitk.robots package when it is importable (kind "aitk"), else the
+    in-repo float64 port (kind "port"; the mounted reference tree ships no engine)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kind = "port"
-    if _real_aitk():
-        kind = "port"  # the adapter to the real package is tests/test_real_aitk.py; timing still uses the port
     per_step_seconds = max(1.0, min(8.0, 150.0 / max(args.steps + args.warmup, 1)))
     vals, tests = [], []
-    sample = ""
+    sample, cores, kind = "", 1, "port"
     for k in range(args.warmup + args.steps):
         r = cpu_throughput(args.config, per_step_seconds if k >= args.warmup else 1.0)
         if k >= args.warmup:
             vals.append(r["world_steps_per_sec"])
             tests.append(r["tests_per_sec"])
-            sample, cores = r["sample"], r["cores"]
+            sample, cores, kind = r["sample"], r["cores"], r["kind"]
     v = sum(vals) / len(vals)
     import aitk_robots_b200 as rb
 
@@ -231,18 +236,335 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "world-steps/sec", "value": v, "unit": "world-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        # a "step" of this arm is a bounded sample; ms_per_step extrapolates it to the full batch
-        "ms_per_step": 1e3 * args.worlds * max(args.gpus, 1) / v, "higher_is_better": True, "scaling": "weak",
+        # a "step" of this arm is a bounded sample of the batch: ms_per_step is that sample's rate
+        # EXTRAPOLATED to the whole N-GPU batch, not a measured duration
+        "ms_per_step": 1e3 * args.worlds * max(args.gpus, 1) / v, "ms_per_step_extrapolated": True,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "ray_segment_tests_per_sec": sum(tests) / len(tests),
         "cpu_baseline": {"value": v, "unit": "world-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.config == "config2" and not args.no_extra:
+        line["config1_as_written"] = config1_as_written()
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank on the CPUs next to its GPU, BEFORE any pinned allocation, so that the
+    host buffers of the end-to-end path are first-touched on the GPU's NUMA node (8 ranks
+    draining pictures into one node's memory is what capped the round-1 aggregate at ~92 GB/s)."""
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info.update({"pci": bus, "numa_node": node, "local_cpus": len(cpus)})
+        if use and node >= 0:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+    except Exception as e:  # no sysfs / no permission: stay where we are
+        info["error"] = str(e)[:80]
+    return info
+
+
+class Bench:
+    """One rank of the GPU arm: shared plumbing of the per-workload measurements."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.numa = bind_to_gpu_numa_node(torch, self.local_rank)
+        if self.world_size > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        import __graft_entry__ as ge
+
+        if self.rank == 0:
+            ge.build()
+        if self.world_size > 1:
+            dist.barrier()
+        import aitk_robots_b200 as rb
+
+        self.rb = rb
+        self.stream = torch.cuda.current_stream()
+        self.sh = self.stream.cuda_stream
+        self.launches = 0
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            self.hbm_peak, self.peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+        else:
+            self.hbm_peak, self.peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            self.ffma_tflops, _ = rb.measure_fp32_peak(self.local_rank, 4096)
+        except Exception:
+            self.ffma_tflops = None
+
+    def barrier(self):
+        if self.world_size > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="max"):
+        """max / sum over ranks of a list of floats."""
+        if self.world_size == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def time_steps(self, eng, flags, steps, warmup, per_launch=False):
+        """K device-timed steps (CUDA events on the launching stream, barrier + synchronize on
+        both sides); returns (total ms of this rank, per-step ms list or None)."""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            eng.step(flags=flags, stream=self.sh)
+        self.barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range((steps + 1) if per_launch else 2)]
+        self.barrier()
+        evs[0].record(self.stream)
+        for k in range(steps):
+            eng.step(flags=flags, stream=self.sh)
+            if per_launch:
+                evs[k + 1].record(self.stream)
+        if not per_launch:
+            evs[1].record(self.stream)
+        self.barrier()
+        self.launches += steps * eng.launch_info()["launches_per_step"]
+        total = evs[0].elapsed_time(evs[-1])
+        return total, ([evs[k].elapsed_time(evs[k + 1]) for k in range(steps)] if per_launch else None)
+
+    def rooflines(self, eng, ms, tests_per_step, executed):
+        """Both rooflines of one launch of `eng` that took `ms`."""
+        B, R = eng.n_worlds, eng.n_robots
+        bytes_read = B * (5 * eng.seg_cap * 4 + 4 + 8 + 3 * R * 24) + B * eng.n_light * eng.n_bulbs * 16
+        bytes_write = B * (2 * R * 24 + R + eng.n_range * 4 + eng.n_camera * eng.cam_h * eng.cam_w * 4
+                           + eng.n_light * 4 + eng.n_smell * 4)
+        alg = bytes_read + bytes_write
+        achieved = alg / (ms * 1e-3) / 1e9
+        hbm = {"achieved": achieved, "peak": self.hbm_peak, "unit": "GB/s", "frac": achieved / self.hbm_peak,
+               "peak_source": self.peak_src, "algorithmic_bytes_per_launch": alg, "bytes_written_per_launch": bytes_write}
+        peak = self.ffma_tflops or NOMINAL_FP32_TFLOPS
+        tf = tests_per_step * FLOPS_PER_TEST / (ms * 1e-3) / 1e12
+        fp32 = {"achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                "peak_source": "measured on this GPU (brs_measure_fp32_peak, dependent FFMA chains)" if self.ffma_tflops
+                else "nominal 148 SMs x 128 lanes x 2 x 1.965 GHz",
+                "peak_nominal": NOMINAL_FP32_TFLOPS, "flops_per_test": FLOPS_PER_TEST,
+                "algorithmic_tests_per_launch": tests_per_step,
+                "note": "frac counts every (ray, segment) pair of the workload at 13 flops (SURVEY.md 8(d): early exits "
+                        "still count); the executed_* keys count what the search loops really ran after the culls"}
+        if executed is not None:
+            ray_t, edge_t = executed
+            fp32["executed_ray_tests_per_launch"] = ray_t
+            fp32["executed_edge_tests_per_launch"] = edge_t
+            fp32["executed_tests_per_sec"] = (ray_t + edge_t) / (ms * 1e-3)
+            fp32["executed_frac"] = (ray_t + edge_t) * FLOPS_PER_TEST / (ms * 1e-3) / 1e12 / peak
+            fp32["culled_share"] = 1.0 - (ray_t + edge_t) / max(tests_per_step, 1)
+        return hbm, fp32
+
+    def workload(self, config, B, steps, warmup, e2e=False, per_launch=False, keep=False):
+        """Device-timed steps of one configuration on every rank (weak scaling: B worlds each).
+        Returns (summary dict on rank 0 else None, engine if keep)."""
+        rb = self.rb
+        scene = make_scene(rb, config, B, self.rank * B)
+        eng = rb.BatchEngine(scene, device=self.local_rank)
+        flags = rb.STEP_ALL
+        tests_per_step = eng.count_tests(flags, self.sh)
+        assert tests_per_step == scene.tests_per_step(), (tests_per_step, scene.tests_per_step())
+        total_ms, launch_ms = self.time_steps(eng, flags, steps, warmup, per_launch)
+        executed = None
+        try:
+            executed = eng.step_counted(flags=flags, stream=self.sh)
+        except Exception:
+            pass
+        total_ms, = self.reduce([total_ms])
+        all_tests, = self.reduce([float(tests_per_step)], "sum")
+        ms = total_ms / steps
+        out = None
+        if self.rank == 0:
+            avg_launch = sum(launch_ms) / len(launch_ms) if launch_ms else ms
+            hbm, fp32 = self.rooflines(eng, avg_launch, tests_per_step, executed)
+            out = {"config": describe(config, scene), "ms_per_step": ms, "avg_launch_ms": avg_launch,
+                   "value": self.world_size * B / (ms * 1e-3), "unit": "world-steps/s",
+                   "ray_segment_tests_per_sec": all_tests / (ms * 1e-3), "ray_segment_tests_per_step": all_tests,
+                   "hbm": hbm, "fp32": fp32, "launch": eng.launch_info(), "scene": scene}
+        if keep:
+            return out, eng, scene
+        eng.close()
+        return out, None, None
+
+
+def pinned(torch, shape, dt):
+    return torch.empty(shape, dtype=dt, pin_memory=True)
+
+
+def e2e_measure(bench, eng, scene, steps):
+    """The same step through brs_step_host: target velocities host->device, every observation
+    device->host, pinned buffers, all inside the timed region."""
+    torch, rb = bench.torch, bench.rb
+    B = eng.n_worlds
+    h_tvel = pinned(torch, (B, eng.n_robots, 3), torch.float64)
+    h_tvel.copy_(torch.from_numpy(scene.target_vel))
+    h_pose = pinned(torch, (B, eng.n_robots, 3), torch.float64)
+    h_stalled = pinned(torch, (B, eng.n_robots), torch.uint8)
+    h_range = pinned(torch, (B, max(eng.n_range, 1)), torch.float32)
+    h_cam = pinned(torch, (B, max(eng.n_camera, 1), max(eng.cam_h, 1), max(eng.cam_w, 1), 4), torch.uint8)
+    h_light = pinned(torch, (B, max(eng.n_light, 1)), torch.float32)
+    h_smell = pinned(torch, (B, max(eng.n_smell, 1)), torch.float32)
+    for t in (h_pose, h_stalled, h_range, h_cam, h_light, h_smell):
+        t.zero_()  # first touch on this rank's (GPU-local) NUMA node
+    h2d = h_tvel.numel() * 8
+    d2h = (h_pose.numel() * 8 + h_stalled.numel() + eng.n_range * B * 4 + eng.n_camera * B * eng.cam_h * eng.cam_w * 4
+           + eng.n_light * B * 4 + eng.n_smell * B * 4)
+    flags = rb.STEP_ALL
+
+    def e2e_step():
+        eng.step_host(flags=flags, target_vel=h_tvel.data_ptr(), pose=h_pose.data_ptr(), stalled=h_stalled.data_ptr(),
+                      range_=h_range.data_ptr() if eng.n_range else 0, camera=h_cam.data_ptr() if eng.n_camera else 0,
+                      light=h_light.data_ptr() if eng.n_light else 0, smell=h_smell.data_ptr() if eng.n_smell else 0,
+                      stream=bench.sh)
+
+    n = max(3, min(steps, 10))
+    for _ in range(3):
+        e2e_step()
+    bench.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(bench.stream)
+    for _ in range(n):
+        e2e_step()
+    e1.record(bench.stream)
+    bench.barrier()
+    bench.launches += n * eng.launch_info()["launches_per_step"]
+    e2e_ms = e0.elapsed_time(e1)
+    # the host ceiling: the same bytes as ONE plain device->host copy per rank, all ranks at
+    # once, no kernel -- what the PCIe links and the host memory system deliver on this box
+    big = h_cam if eng.n_camera else h_pose
+    src = eng.tensor("camera" if eng.n_camera else "pose")
+    for _ in range(2):
+        big.copy_(src.view(big.shape), non_blocking=True)
+    bench.barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(bench.stream)
+    for _ in range(n):
+        big.copy_(src.view(big.shape), non_blocking=True)
+    c1.record(bench.stream)
+    bench.barrier()
+    copy_ms = c0.elapsed_time(c1)
+    e2e_ms, copy_ms = bench.reduce([e2e_ms, copy_ms])
+    ws = bench.world_size
+    nbytes = big.numel() * big.element_size()
+    return {"value": ws * B * n / (e2e_ms * 1e-3), "unit": "world-steps/s", "h2d_bytes_per_step": int(h2d) * ws,
+            "d2h_bytes_per_step": int(d2h) * ws, "ms_per_step": e2e_ms / n,
+            "api": "brs_step_host (C ABI, pinned host buffers; kernel of chunk c+1 overlaps the copies of chunk c)",
+            "achieved_d2h_gbs": d2h * ws * n / (e2e_ms * 1e-3) / 1e9,
+            "host_ceiling_gbs": nbytes * ws * n / (copy_ms * 1e-3) / 1e9,
+            "host_ceiling_note": "aggregate GB/s of one plain cudaMemcpyAsync D2H of the pictures per rank, all ranks "
+                                 "at once, same pinned buffers",
+            "numa": bench.numa}
+
+
+def gather_measure(bench, eng, steps, name, overlap):
+    """World.step + the observation all-gather (the path's only collective), in place: the
+    kernels write this rank's slice of the gather buffer (brs_bind_output).  `overlap`: two
+    gather buffers, the all-gather of step t runs on NCCL's stream while step t+1 computes."""
+    torch, dist, rb = bench.torch, bench.dist, bench.rb
+    B, ws, rank = eng.n_worlds, bench.world_size, bench.rank
+    local = eng.tensor(name)
+    nbuf = 2 if overlap else 1
+    full = [torch.empty((B * ws,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for _ in range(nbuf)]
+    mine = [f[rank * B:(rank + 1) * B] for f in full]
+    bindable = name in ("camera", "range", "light", "smell")
+    works = [None] * nbuf
+
+    def one(t):
+        b = t % nbuf
+        if works[b] is not None:
+            works[b].wait()  # the buffer's previous gather is done before the kernel overwrites its slice
+            works[b] = None
+        if bindable:
+            eng.bind_output(name, mine[b])
+        eng.step(flags=rb.STEP_ALL, stream=bench.sh)
+        if not bindable:
+            mine[b].copy_(local)
+        if overlap:
+            works[b] = dist.all_gather_into_tensor(full[b], mine[b], async_op=True)
+        else:
+            dist.all_gather_into_tensor(full[b], mine[b])
+
+    for t in range(4):
+        one(t)
+    for w in works:
+        if w is not None:
+            w.wait()
+    works = [None] * nbuf
+    bench.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(bench.stream)
+    for t in range(steps):
+        one(t)
+    for w in works:
+        if w is not None:
+            w.wait()
+    g1.record(bench.stream)
+    bench.barrier()
+    bench.launches += steps * eng.launch_info()["launches_per_step"]
+    if bindable:
+        eng.bind_output(name, None)
+    ms, = bench.reduce([g0.elapsed_time(g1) / steps])
+    per_rank = int(mine[0].numel() * mine[0].element_size())
+    inbound = per_rank * (ws - 1)
+    del full, mine
+    torch.cuda.empty_cache()
+    return {"observation": name, "bytes_per_rank_per_step": per_rank, "ms_per_step_with_gather": ms, "in_place": bindable,
+            "overlapped_with_next_step": overlap,
+            "nvlink_floor_ms": inbound / 900e9 * 1e3,
+            "nvlink_floor_note": "(N-1) x bytes_per_rank inbound per GPU / 900 GB/s per direction (NVLink 5)"}
+
+
+def summarize(w):
+    """Sub-object of the JSON line for one extra workload."""
+    return {"workload": w["config"]["workload"], "worlds_per_gpu": w["config"]["worlds_per_gpu"],
+            "ms_per_step": w["ms_per_step"], "world_steps_per_sec": w["value"],
+            "ray_segment_tests_per_sec": w["ray_segment_tests_per_sec"],
+            "hbm_frac": w["hbm"]["frac"], "fp32_frac": w["fp32"]["frac"],
+            "fp32_executed_frac": w["fp32"].get("executed_frac"), "culled_share": w["fp32"].get("culled_share"),
+            "executed_tests_per_sec": w["fp32"].get("executed_tests_per_sec"),
+            "launch": {k: w["launch"][k] for k in ("path", "launches_per_step", "threads", "ctas", "smem_bytes")}}
+
+
+def pipe_utilisation(config):
+    """ncu pipe counters of this workload's step kernel from the committed profile summary
+    (profiles/r2/pipes.json, written by tools/ncu_pipes.py from the same commit's capture):
+    a bench run cannot read hardware counters itself."""
+    pth = os.path.join(ROOT, "profiles", "r2", "pipes.json")
+    if os.path.exists(pth):
+        try:
+            return json.load(open(pth)).get(config)
+        except Exception:
+            return None
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,6 +577,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-large-batch", action="store_true",
                     help="skip the supplementary run at 4x the worlds (shows the launch prologue/tail share)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the other BASELINE.json configurations (config1/3/4 sub-objects of the default line)")
     ap.add_argument("--gather", action="store_true", help="also time the optional NCCL observation all-gather")
     args = ap.parse_args()
     if not args.worlds:
@@ -262,227 +586,144 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import __graft_entry__ as ge
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if rank == 0:
-        ge.build()
-    if world_size > 1:
-        dist.barrier()
-    import aitk_robots_b200 as rb
-
+    bench = Bench(args)
+    rb, torch = bench.rb, bench.torch
+    rank, world_size, local_rank = bench.rank, bench.world_size, bench.local_rank
     B = args.worlds
-    scene = make_scene(rb, args.config, B, rank * B)
-    eng = rb.BatchEngine(scene, device=local_rank)
-    stream = torch.cuda.current_stream()
-    sh = stream.cuda_stream
-    flags = rb.STEP_ALL
-    tests_per_step = eng.count_tests(flags, sh)
-    assert tests_per_step == scene.tests_per_step(), (tests_per_step, scene.tests_per_step())
+    extras = args.config == "config2" and not args.no_extra
 
-    def barrier():
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing: K steps, one kernel launch each -------------------
-    for _ in range(max(args.warmup, 3)):
-        eng.step(flags=flags, stream=sh)
-    barrier()
+    # ---- the headline workload: device-resident timing, one launch per step -----------
     sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("BRS_BENCH_NO_CLOCKS") else None
     if sampler:
         sampler.start()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    evs[0].record(stream)
-    for k in range(args.steps):
-        eng.step(flags=flags, stream=sh)
-        evs[k + 1].record(stream)
-    barrier()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
-
+    head, eng, scene = bench.workload(args.config, B, args.steps, args.warmup, per_launch=True, keep=True)
     # ---- end to end: host buffers in, host buffers out, through the C ABI ----------
-    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)  # noqa: E731
-    h_tvel = pin((B, eng.n_robots, 3), torch.float64)
-    h_tvel.copy_(torch.from_numpy(scene.target_vel))
-    h_pose = pin((B, eng.n_robots, 3), torch.float64)
-    h_stalled = pin((B, eng.n_robots), torch.uint8)
-    h_range = pin((B, max(eng.n_range, 1)), torch.float32)
-    h_cam = pin((B, max(eng.n_camera, 1), max(eng.cam_h, 1), max(eng.cam_w, 1), 4), torch.uint8)
-    h_light = pin((B, max(eng.n_light, 1)), torch.float32)
-    h_smell = pin((B, max(eng.n_smell, 1)), torch.float32)
-    h2d = h_tvel.numel() * 8
-    d2h = (h_pose.numel() * 8 + h_stalled.numel() + eng.n_range * B * 4 + eng.n_camera * B * eng.cam_h * eng.cam_w * 4
-           + eng.n_light * B * 4 + eng.n_smell * B * 4)
-
-    def e2e_step():
-        eng.step_host(flags=flags, target_vel=h_tvel.data_ptr(), pose=h_pose.data_ptr(), stalled=h_stalled.data_ptr(),
-                      range_=h_range.data_ptr() if eng.n_range else 0, camera=h_cam.data_ptr() if eng.n_camera else 0,
-                      light=h_light.data_ptr() if eng.n_light else 0, smell=h_smell.data_ptr() if eng.n_smell else 0,
-                      stream=sh)
-
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e = e2e_measure(bench, eng, scene, args.steps)
     clocks = sampler.stop() if sampler else None  # sampled over the device-timed and the end-to-end regions
-
-    # ---- optional observation all-gather (the only collective of the path) ---------
     gather = None
     if args.gather and world_size > 1:
-        # the kernels write this rank's slice of the gather buffer directly (brs_bind_output),
-        # the all-gather is in place: no staging copy precedes the collective
-        name = "camera" if eng.n_camera else "range"
-        local = eng.tensor(name)
-        full = torch.empty((B * world_size,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        mine = full[rank * B:(rank + 1) * B]
-        eng.bind_output(name, mine)
-        for _ in range(3):
-            eng.step(flags=flags, stream=sh)
-            dist.all_gather_into_tensor(full, mine)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(args.steps):
-            eng.step(flags=flags, stream=sh)
-            dist.all_gather_into_tensor(full, mine)
-        g1.record(stream)
-        barrier()
-        eng.bind_output(name, None)
-        gather = {"observation": name, "bytes_per_rank_per_step": int(mine.numel() * mine.element_size()),
-                  "ms_per_step_with_gather": g0.elapsed_time(g1) / args.steps, "in_place": True}
+        gather = gather_measure(bench, eng, args.steps, "camera" if eng.n_camera else "range", overlap=False)
+    eng.close()
+    eng = None
 
-    # ---- max over ranks ---------------------------------------------------------------
-    t = torch.tensor([total_ms, e2e_ms, float(tests_per_step)], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms, all_tests = float(tmax[0]), float(tmax[1]), float(tsum[2])
-    else:
-        all_tests = float(tests_per_step)
-
+    line = None
     if rank == 0:
-        ms_per_step = total_ms / args.steps
-        value = world_size * B * args.steps / (total_ms * 1e-3)
-        tests_per_sec = all_tests * args.steps / (total_ms * 1e-3)
-        e2e_value = world_size * B * e2e_steps / (e2e_ms * 1e-3)
-        # roofline of the (only) kernel: algorithmic HBM bytes per launch, this rank
-        R = eng.n_robots
-        bytes_read = B * (5 * eng.seg_cap * 4 + 4 + 8 + 3 * R * 24) + B * eng.n_light * eng.n_bulbs * 16
-        bytes_write = B * (2 * R * 24 + R + eng.n_range * 4 + eng.n_camera * eng.cam_h * eng.cam_w * 4
-                           + eng.n_light * 4 + eng.n_smell * 4)
-        alg_bytes = bytes_read + bytes_write
-        avg_launch_ms = sum(launch_ms) / len(launch_ms)
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
-        else:
-            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
-        try:
-            ffma_tflops, _ = rb.measure_fp32_peak(local_rank, 4096)
-        except Exception:
-            ffma_tflops = None
-        fp32_tflops = tests_per_step * FLOPS_PER_TEST / (avg_launch_ms * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.config)
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        hbm = {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes}
+        hbm, fp32 = head["hbm"], head["fp32"]
         try:
             # context: what a plain streaming-store kernel reaches on this GPU (the path is write-only)
             wc = rb.measure_write_bw(local_rank, 512 << 20, 0, 5)
             hbm["write_only_ceiling_gbs"] = wc
-            hbm["frac_of_write_only_ceiling"] = achieved / wc
+            hbm["frac_of_write_only_ceiling"] = hbm["achieved"] / wc
         except Exception:
             pass
-        fp32 = {"achieved": fp32_tflops, "peak": ffma_tflops or NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
-                "frac": fp32_tflops / (ffma_tflops or NOMINAL_FP32_TFLOPS),
-                "peak_source": "measured on this GPU (brs_measure_fp32_peak, dependent FFMA chains)" if ffma_tflops
-                else "nominal 148 SMs x 128 lanes x 2 x 1.965 GHz",
-                "peak_nominal": NOMINAL_FP32_TFLOPS, "flops_per_test": FLOPS_PER_TEST,
-                "algorithmic_tests_per_launch": tests_per_step}
-        # the bound of this workload is the roofline it sits closer to: pictures are HBM-write
-        # bound (config2), ray-heavy worlds with small pictures FP32-issue bound (config4/5)
-        dom = hbm if hbm["frac"] >= fp32["frac"] else fp32
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r2", "traffic_%s.json" % args.config)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        pipes = pipe_utilisation(args.config)
+        if pipes:
+            fp32["ncu_pipes"] = pipes
+        # the bound of this workload is the roofline it sits closer to by EXECUTED work: pictures
+        # are HBM-write bound (config2), ray-heavy worlds with small pictures issue bound (config4/5)
+        fp_exec = fp32.get("executed_frac", fp32["frac"])
+        dom = hbm if hbm["frac"] >= fp_exec else fp32
         roofline = {"bound": "hbm" if dom is hbm else "fp32", "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "peak_source": dom["peak_source"],
-                    "kernel": "brs_step_kernel", "avg_launch_ms": avg_launch_ms, "hbm": hbm, "fp32": fp32}
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": dom["peak_source"], "kernel": "brs_step_kernel" if head["launch"]["path"].startswith("fused")
+                    else ("brs_solo_kernel" if head["launch"]["path"].startswith("solo") else "brs_wide_kernel"),
+                    "avg_launch_ms": head["avg_launch_ms"], "hbm": hbm, "fp32": fp32}
         line = {
-            "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world_size,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": "world-steps/sec", "value": head["value"], "unit": "world-steps/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(describe(args.config, scene),
-                           l2="no explicit flush: every step streams %.0f MB of fresh observations through a 126 MB L2"
-                              % (bytes_write / 1e6),
-                           precision="FP32 ray search + FP64 winner refinement, FP64 motion/collision",
-                           launch=eng.launch_info()),
-            "ray_segment_tests_per_sec": tests_per_sec,
-            "ray_segment_tests_per_step": all_tests,
+            "config": head["config"],
+            "l2": "no explicit flush: every step streams %.0f MB of fresh observations through a 126 MB L2"
+                  % (hbm["bytes_written_per_launch"] / 1e6),
+            "precision": "FP32 ray search + FP64 winner refinement, FP64 motion/collision",
+            "launch": head["launch"],
+            "ray_segment_tests_per_sec": head["ray_segment_tests_per_sec"],
+            "ray_segment_tests_per_step": head["ray_segment_tests_per_step"],
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": int(h2d) * world_size,
-                    "d2h_bytes_per_step": int(d2h) * world_size, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "brs_step_host (C ABI, pinned host buffers)"},
-            "gpu_launches": args.steps,
+            "e2e": e2e,
             "clocks": clocks,
         }
         if gather:
             line["gather"] = gather
-        if world_size == 1 and not args.no_large_batch and 4 * alg_bytes < 16e9:
-            # supplementary: the same workload at 4x the worlds.  A launch of the named size lasts
-            # ~0.1 ms, of which the pipeline fill (first tile of every CTA) and the tail are a fixed
-            # ~20 us; the larger batch shows the kernel's steady-state rate.  Not the headline.
-            eng.close()
-            eng = None
-            big = rb.BatchEngine(make_scene(rb, args.config, 4 * B, 50_000_000), device=local_rank)
-            for _ in range(3):
-                big.step(flags=flags, stream=sh)
+
+    # ---- the other BASELINE.json configurations, same run (sub-objects of the line) ----
+    if world_size == 1 and not args.no_large_batch and rank == 0 and 4 * line["roofline"]["hbm"]["algorithmic_bytes_per_launch"] < 16e9:
+        # supplementary: the same workload at 4x the worlds.  A launch of the named size lasts
+        # ~0.1 ms, of which the pipeline fill (first tile of every CTA) and the tail are a fixed
+        # ~20 us; the larger batch shows the kernel's steady-state rate.  Not the headline.
+        big, _, _ = bench.workload(args.config, 4 * B, args.steps, 3)
+        line["large_batch"] = {"worlds_per_gpu": 4 * B, "ms_per_step": big["ms_per_step"], "value": big["value"],
+                               "hbm_frac": big["hbm"]["frac"], "fp32_frac": big["fp32"]["frac"]}
+    if extras:
+        ex = {}
+        steps_x = max(5, min(args.steps, 20))
+        if world_size == 1:
+            # config 1 on the GPU: ONE world, 1000 sequential World.steps (launch-latency bound)
+            scene1 = make_scene(rb, "config1", 1, 0)
+            e1 = rb.BatchEngine(scene1, device=local_rank)
+            for _ in range(20):
+                e1.step(stream=bench.sh)
             torch.cuda.synchronize()
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            b0.record(stream)
-            for _ in range(args.steps):
-                big.step(flags=flags, stream=sh)
-            b1.record(stream)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a0.record(bench.stream)
+            for _ in range(1000):
+                e1.step(stream=bench.sh)
+            a1.record(bench.stream)
             torch.cuda.synchronize()
-            bms = b0.elapsed_time(b1) / args.steps
-            line["large_batch"] = {"worlds_per_gpu": 4 * B, "ms_per_step": bms, "value": 4 * B / (bms * 1e-3),
-                                   "hbm_frac": 4 * alg_bytes / (bms * 1e-3) / 1e9 / hbm_peak,
-                                   "fp32_frac": 4 * tests_per_step * FLOPS_PER_TEST / (bms * 1e-3) / 1e12
-                                   / (ffma_tflops or NOMINAL_FP32_TFLOPS)}
-            big.close()
+            wall = time.perf_counter() - t0
+            bench.launches += 1000
+            ex["config1"] = {"workload": describe("config1", scene1)["workload"], "worlds": 1, "steps": 1000,
+                             "gpu_seconds_for_1000_steps": a0.elapsed_time(a1) * 1e-3, "host_wall_seconds": wall,
+                             "world_steps_per_sec": 1000.0 / (a0.elapsed_time(a1) * 1e-3),
+                             "note": "one world cannot fill a GPU: this is launch latency; the batched path is config1 x 4096"}
+            e1.close()
+            w, _, _ = bench.workload("config1", 4096, steps_x, 3)
+            ex["config1_x4096"] = summarize(w)
+            w, _, _ = bench.workload("config3", DEFAULT_WORLDS["config3"], steps_x, 3)
+            ex["config3"] = summarize(w)
+        # config 4: 1,048,576 worlds split over the ranks (N = 1: one eighth, the 8-GPU shard)
+        per_rank = (1 << 20) // max(world_size, 8 if world_size == 1 else world_size)
+        w, e4, s4 = bench.workload("config4", per_rank, steps_x, 3, keep=True)
+        if rank == 0:
+            ex["config4"] = summarize(w)
+            ex["config4"]["worlds_total"] = per_rank * world_size
+            ex["config4"]["sharding"] = ("1,048,576 worlds / %d GPUs" % world_size) if world_size > 1 \
+                else "one GPU's shard of the 8-GPU split (131,072 worlds)"
+            pipes = pipe_utilisation("config4")
+            if pipes:
+                ex["config4"]["ncu_pipes"] = pipes
+        if world_size > 1:
+            g_serial = gather_measure(bench, e4, steps_x, "camera", overlap=False)
+            g_over = gather_measure(bench, e4, steps_x, "camera", overlap=True)
+            g_small = gather_measure(bench, e4, steps_x, "pose", overlap=True)
+            if rank == 0:
+                ex["config4"]["gather_pictures"] = g_serial
+                ex["config4"]["gather_pictures_overlapped"] = g_over
+                ex["config4"]["gather_poses_only"] = g_small
+        e4.close()
+        if rank == 0:
+            line["configs"] = ex
+    if rank == 0:
+        line["gpu_launches"] = bench.launches
         if not args.no_cpu_baseline and world_size == 1:
             r = cpu_throughput(args.config, args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["world_steps_per_sec"], "unit": "world-steps/s", "cores": r["cores"],
-                                    "kind": "port", "sample": r["sample"],
+                                    "kind": r["kind"], "sample": r["sample"],
                                     "ray_segment_tests_per_sec": r["tests_per_sec"]}
+            if extras:
+                line["configs"]["config1_cpu_as_written"] = config1_as_written()
+        for v in line.get("configs", {}).values():
+            v.pop("scene", None)
         print(json.dumps(line))
-    if eng is not None:
-        eng.close()
     if world_size > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        bench.dist.barrier()
+        bench.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

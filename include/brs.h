@@ -205,7 +205,8 @@ int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* worker
  * *wide = 0: the fused kernel (one launch per step; Robot.step of tile n+1 overlaps the rays
  * of tile n inside a CTA), 1: the wide path (prep kernel + step kernel chained with
  * programmatic dependent launch; see csrc/brs_wide.cuh), 2: the fused kernel fed by the prep
- * kernel (its helper team skips the float64 pose proposal).  All produce identical bits.
+ * kernel (its helper team skips the float64 pose proposal), 3: the solo path (one warp per
+ * one-robot camera world, one launch; see csrc/brs_solo.cuh).  All produce identical bits.
  * *launches_per_step = kernels one brs_step enqueues. */
 int brs_path_info(brs_engine* e, int* wide, int* launches_per_step);
 

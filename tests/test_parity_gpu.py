@@ -221,8 +221,12 @@ def test_culling_and_tiling_never_change_results(maker):
     scene = maker()
     # the base run is the fused kernel; BRS_WIDE=1 variants run the two-kernel wide path
     # (one-warp teams, wider teams, several worlds per tile, walls from L2, no PDL)
-    base = _outputs(scene, 3, {"BRS_WIDE": "0"})
-    for env in ({"BRS_WIDE": "0", "BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_WIDE": "0", "BRS_TW": "1"},
+    base = _outputs(scene, 3, {"BRS_WIDE": "0", "BRS_SOLO": "0"})
+    # (BRS_SOLO=1 only takes effect for the shapes the solo path accepts: config 4 here)
+    for env in ({"BRS_SOLO": "1"}, {"BRS_SOLO": "1", "BRS_SOLO_CTAS": "8", "BRS_NO_CONE": "1"},
+                {"BRS_SOLO": "1", "BRS_SOLO_CTAS": "4", "BRS_SOLO_MAX_CTAS": "1", "BRS_NO_RANGE_CULL": "1"},
+                {"BRS_SOLO": "1", "BRS_SOLO_CTAS": "7"}, {"BRS_SOLO": "1", "BRS_SOLO_CTAS": "5"},
+                {"BRS_WIDE": "0", "BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_WIDE": "0", "BRS_TW": "1"},
                 {"BRS_WIDE": "0", "BRS_TW": "5", "BRS_BIG": "1"},
                 {"BRS_WIDE": "0", "BRS_NH": "2"}, {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "1"},
                 {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
@@ -233,13 +237,111 @@ def test_culling_and_tiling_never_change_results(maker):
                 {"BRS_WIDE": "1", "BRS_WNT": "256", "BRS_WTW": "5", "BRS_WBIG": "1"},
                 {"BRS_WIDE": "1", "BRS_PDL": "0", "BRS_NO_CONE": "1"},
                 {"BRS_WIDE": "1", "BRS_NR": "1", "BRS_GROUP_MIN": "1000"}):
-        other = _outputs(scene, 3, env)
+        other = _outputs(scene, 3, dict({"BRS_SOLO": "0"}, **env))
         for k in base:
             if k in ("range", "light") and env.get("BRS_GROUP_MIN"):
                 # group path vs direct path are two FP32 formulations of the same search
                 np.testing.assert_allclose(other[k], base[k], rtol=1e-6, err_msg=str((k, env)))
             else:
                 assert np.array_equal(other[k], base[k]), (k, env)
+
+
+def _with_env(env, fn):
+    import os
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("cam_w,cam_h", [(64, 32), (32, 16), (128, 20)])
+def test_solo_path_matches_the_oracle(cam_w, cam_h):
+    """The warp-per-world path (one robot, one camera; csrc/brs_solo.cuh) against the oracle:
+    maze and random walls, batches that are not a multiple of its PREP pass, ragged and empty
+    worlds, columns that see nothing (short camera range), robots driven into walls."""
+    for variant in ("maze", "random"):
+        scene = rb.scenes.config4(n_worlds=41, variant=variant, cam_w=cam_w, cam_h=cam_h)
+        scene.seg_count[3] = 0
+        scene.seg_count[5] = 37
+        scene.target_vel[:, :, 0] = np.linspace(-2.0, 2.0, 41)[:, None]
+
+        def run():
+            eng = rb.BatchEngine(scene)
+            assert eng.launch_info()["path"].startswith("solo"), eng.launch_info()
+            eng.close()
+            return parity.compare(scene, n_steps=4, worlds=range(0, 41, 3))
+
+        stats = _with_env({"BRS_SOLO": "1"}, run)
+        assert stats["pixel_mismatch"] <= 0.002 * stats["pixels"]
+    # a camera that cannot see the far walls leaves blank (0, 0, 0, 0) columns
+    scene = rb.scenes.config4(n_worlds=20, variant="maze", cam_w=cam_w, cam_h=cam_h)
+    for spec in scene.robots[0].devices:
+        if isinstance(spec, rb.CameraSpec):
+            spec.max_range = 30.0
+    stats = _with_env({"BRS_SOLO": "1"}, lambda: parity.compare(scene, n_steps=2))
+    assert stats["pixel_mismatch"] <= 0.002 * stats["pixels"]
+    # 60 steps at full speed: robots stall against the maze walls, flags and poses exact
+    scene = rb.scenes.config4(n_worlds=16, cam_w=cam_w, cam_h=cam_h)
+    scene.target_vel[:, :, 0] = 2.0
+    stats = _with_env({"BRS_SOLO": "1"}, lambda: parity.compare(scene, n_steps=60, camera=False))
+    assert stats["max_pose_err"] < 1e-9
+
+
+def test_solo_path_step_flags():
+    """Move-only and camera-only steps of the solo path equal the fused kernel's, bit for bit."""
+    scene = rb.scenes.config4(n_worlds=100)
+    scene.target_vel[:, :, 0] = 2.0
+
+    def run():
+        eng = rb.BatchEngine(scene)
+        outs = []
+        for flags in (rb.STEP_CAMERA, rb.STEP_MOVE, rb.STEP_MOVE, rb.STEP_SENSE, rb.STEP_CAMERA, rb.STEP_ALL):
+            eng.step(flags=flags)
+            eng.synchronize()
+            outs.append({k: eng.download(k) for k in ("pose", "vel", "stalled", "camera")})
+        eng.close()
+        return outs
+
+    a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0"}, run)
+    b = _with_env({"BRS_SOLO": "1"}, run)
+    for x, y in zip(a, b):
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+
+
+def test_solo_path_sky_gradient():
+    """Non-flat sky / ground rows on the solo path (its generic paint loop)."""
+    from oracle import aitk_oracle as orc
+    from oracle import scene_adapter as sa
+
+    scene = rb.scenes.config4(n_worlds=6)
+    sky_grad, gnd_grad = (40, 20, 100), (30, 60, 10)
+    old = (orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD)
+    orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD = sky_grad, gnd_grad
+    try:
+        def run():
+            eng = rb.BatchEngine(scene, sky_grad=sky_grad, ground_grad=gnd_grad)
+            assert eng.launch_info()["path"].startswith("solo")
+            eng.step()
+            eng.synchronize()
+            cam = eng.download("camera")
+            eng.close()
+            return cam
+
+        cam = _with_env({"BRS_SOLO": "1"}, run)
+        for i in range(6):
+            ref = np.array(sa.step_and_observe(scene, i, 1)["camera"][0], dtype=np.uint8)
+            diff = np.any(cam[i, 0] != ref, axis=2)
+            assert diff.any(axis=0).sum() <= 1, i
+    finally:
+        orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD = old
 
 
 def test_wide_fov_camera_has_no_cone():
