@@ -9,6 +9,8 @@
 #include "brs_wide.cuh"
 #include "brs_solo.cuh"
 
+#include <sched.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +44,10 @@ struct brs_engine {
   void* buf[BRS_BUF_COUNT_] = {};
   size_t stride[BRS_BUF_COUNT_] = {};  // bytes per world
   void* bound[BRS_BUF_COUNT_] = {};
+  RobotDev h_robot0;      // host copies of the first robot / camera / group descriptors and row colours
+  CameraDev h_camera0;    // (the solo path passes them in the kernel parameters)
+  GroupDev h_group0;
+  uint32_t h_sky0 = 0, h_gnd0 = 0;
   RobotDev* d_robots = nullptr;
   RangeDev* d_ranges = nullptr;
   CameraDev* d_cameras = nullptr;
@@ -74,8 +80,17 @@ struct brs_engine {
   const void* w_kfn = nullptr;
   // the solo path (brs_solo.cuh): one warp per one-robot camera world, one launch
   bool solo = false;
-  int sNT = 128, s_grid = 1, s_smem = 0, s_warps_per_sm = 0;
+  int sNT = 128, s_grid = 1, s_smem = 0, s_warps_per_sm = 0, solo_interleave = 1;
   const void* s_kfn = nullptr;
+  int s_ctas_per_sm = 1, f_ctas_per_sm = 1, w_ctas_per_sm = 1;
+  // brs_step_host: chunked pipeline (kernel of chunk c+1 overlaps the device->host copies of chunk c)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[8] = {}, ev_copied = nullptr;
+  int host_chunks = 4;
+  // kernel parameters cached per step-flags value (everything but dt and the rebindable outputs is fixed at create)
+  KParams kp_cache;
+  unsigned kp_flags = 0xffffffffu;
+  bool kp_wide = false;
 };
 
 static int pow2floor(int x) {
@@ -367,6 +382,11 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   for (int j = 1; j < e->cam_h; ++j)
     if (rowsky[j] != rowsky[0] || rowgnd[j] != rowgnd[0]) e->flat_rows = 0;
   int rc;
+  memset(&e->h_robot0, 0, sizeof(RobotDev)); memset(&e->h_camera0, 0, sizeof(CameraDev)); memset(&e->h_group0, 0, sizeof(GroupDev));
+  if (!rdev.empty()) e->h_robot0 = rdev[0];
+  if (!cdev.empty()) e->h_camera0 = cdev[0];
+  if (!groups.empty()) e->h_group0 = groups[0];
+  e->h_sky0 = rowsky[0]; e->h_gnd0 = rowgnd[0];
   if ((rc = to_device(&e->d_robots, rdev)) || (rc = to_device(&e->d_ranges, gdev)) ||
       (rc = to_device(&e->d_cameras, cdev)) || (rc = to_device(&e->d_lights, ldev)) ||
       (rc = to_device(&e->d_smells, sdev)) || (rc = to_device(&e->d_camcs, camcs)) ||
@@ -513,6 +533,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     return fail(BRS_ERR_CUDA, std::string("brs_create: kernel does not fit: ") + cudaGetErrorString(ce));
   }
   nb = std::min(nb, env_int("BRS_MAX_CTAS_PER_SM", 32));
+  e->f_ctas_per_sm = nb;
   e->grid = std::max(1, std::min(e->n_tiles, nb * e->sm_count));
   e->fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
 
@@ -591,12 +612,14 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       wide_ok = ce == cudaSuccess && wnb >= 1;
       if (!wide_ok) cudaGetLastError();
     }
+    e->w_ctas_per_sm = std::max(wnb, 1);
     e->w_grid = std::max(1, std::min(e->w_tiles, std::max(wnb, 1) * e->sm_count));
     // which path: the fused kernel overlaps Robot.step with the rays inside a CTA, which pays
     // when a launch has few tiles per CTA (config 2: 4096 picture-bound worlds); the wide path
     // needs enough worlds to fill every SM with independent teams several times over
-    const bool auto_wide = cfg->n_worlds >= env_int("BRS_WIDE_MIN_WORLDS", 16384);
-    e->wide = wide_ok && env_int("BRS_WIDE", auto_wide ? 1 : 0) != 0;
+    // (measured, profiles/r2: the wide path never beat the fused kernel -- config 4 0.60 vs 0.53 ms,
+    //  config 3 0.26 vs 0.20 ms -- so it is opt-in; the solo path below took over its role)
+    e->wide = wide_ok && env_int("BRS_WIDE", 0) != 0;
     e->pdl = env_int("BRS_PDL", 1) != 0;
     e->prep_fused = wide_ok && !e->wide && env_int("BRS_PREP", 0) != 0;
     if (wide_ok) {
@@ -643,13 +666,24 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       if (ok) {
         snb = std::min(snb, env_int("BRS_SOLO_MAX_CTAS", 32));
         e->s_warps_per_sm = snb * (e->sNT / 32);
+        e->s_ctas_per_sm = snb;
         const int want = (cfg->n_worlds + (e->sNT / 32) - 1) / (e->sNT / 32);  // at least one world per warp
         e->s_grid = std::max(1, std::min(want, snb * e->sm_count));
         const bool auto_solo = cfg->n_worlds >= env_int("BRS_SOLO_MIN_WORLDS", 4 * e->s_warps_per_sm * e->sm_count);
         e->solo = env_int("BRS_SOLO", auto_solo ? 1 : 0) != 0;
+        e->solo_interleave = env_int("BRS_SOLO_INTERLEAVE", 1) != 0;
         if (e->solo) { e->wide = false; e->prep_fused = false; }
       }
     }
+  }
+  // ---- brs_step_host pipeline: a copy stream and the events that chain it to the caller's
+  e->host_chunks = std::max(1, std::min(8, env_int("BRS_HOST_CHUNKS", cfg->n_worlds >= 8192 ? 4 : 1)));
+  ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 8 && ce == cudaSuccess; ++k) ce = cudaEventCreateWithFlags(&e->ev_chunk[k], cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming);
+  if (ce != cudaSuccess) {
+    brs_destroy(e);
+    return fail(BRS_ERR_CUDA, std::string("brs_create: stream / event creation failed: ") + cudaGetErrorString(ce));
   }
   *out = e;
   return BRS_OK;
@@ -691,6 +725,10 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_rowgnd);
   cudaFree(e->d_ws);
   cudaFree(e->d_counters);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (int k = 0; k < 8; ++k)
+    if (e->ev_chunk[k]) cudaEventDestroy(e->ev_chunk[k]);
+  if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   delete e;
   return BRS_OK;
 }
@@ -743,7 +781,22 @@ extern "C" int brs_download(brs_engine* e, int which, void* host, int first_worl
 
 // Kernel parameters of one step: everything but flags, dt and the (rebindable) output
 // pointers is fixed at brs_create.
+static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide);
 static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide) {
+  if (e->kp_flags != flags || e->kp_wide != wide) {
+    fill_params_uncached(e, e->kp_cache, time_step, flags, wide);
+    e->kp_flags = flags;
+    e->kp_wide = wide;
+  }
+  p = e->kp_cache;
+  p.dt = time_step;
+  p.range_out = (float*)cur(e, BRS_BUF_RANGE);
+  p.cam_out = (uint8_t*)cur(e, BRS_BUF_CAMERA);
+  p.light_out = (float*)cur(e, BRS_BUF_LIGHT);
+  p.smell_out = (float*)cur(e, BRS_BUF_SMELL);
+  p.counters = e->counting ? e->d_counters : nullptr;
+}
+static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide) {
   const brs_config& c = e->cfg;
   memset(&p, 0, sizeof(p));
   p.n_worlds = c.n_worlds; p.n_robots = c.n_robots; p.seg_cap = c.seg_cap; p.n_bulbs = c.n_bulbs;
@@ -803,27 +856,48 @@ static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned fl
   p.phase = e->d_phase;
   p.wsg = e->d_ws;
   p.counters = e->counting ? e->d_counters : nullptr;
+  p.s_robot = e->h_robot0; p.s_camera = e->h_camera0; p.s_group = e->h_group0;
+  p.s_sky = e->h_sky0; p.s_gnd = e->h_gnd0;
+  p.solo_interleave = e->solo_interleave;
 }
 
-extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
-  if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
-  if (!(flags & BRS_STEP_ALL)) return BRS_OK;
-  CK(cudaSetDevice(e->cfg.device));
+// One World.step over worlds [first, first + n): every buffer has `world` as its leading
+// dimension, so a sub-range is the same kernel on shifted base pointers.
+static int launch_range(brs_engine* e, int first, int n, double time_step, unsigned flags, void* stream) {
   KParams p;
   fill_params(e, p, time_step, flags, e->wide);
+  const brs_config& c = e->cfg;
+  int grid = e->solo ? e->s_grid : e->wide ? e->w_grid : e->grid;
+  if (first != 0 || n != c.n_worlds) {
+    const size_t R = c.n_robots, f = (size_t)first;
+    p.seg += f * 5 * c.seg_cap; p.seg_count += f; p.world_size += 2 * f;
+    p.bulbs += f * c.n_bulbs * 4; p.grid += f * c.grid_w * c.grid_h;
+    p.pose += f * R * 3; p.vel += f * R * 3; p.tvel += f * R * 3; p.stalled += f * R;
+    p.range_out += f * c.n_range; p.cam_out += f * e->stride[BRS_BUF_CAMERA];
+    p.light_out += f * c.n_light; p.smell_out += f * c.n_smell;
+    if (p.wsg) p.wsg += f * R * BRS_WS_STRIDE;
+    p.n_worlds = n;
+    p.n_tiles = (n + p.TW - 1) / p.TW;
+    if (e->solo) {
+      const int wpc = e->sNT / 32;
+      grid = std::max(1, std::min((n + wpc - 1) / wpc, e->s_ctas_per_sm * e->sm_count));
+    } else {
+      grid = std::max(1, std::min(p.n_tiles, (e->wide ? e->w_ctas_per_sm : e->f_ctas_per_sm) * e->sm_count));
+    }
+  }
   void* args[] = {(void*)&p};
   if (e->solo) {
-    CK(cudaLaunchKernel(e->s_kfn, dim3(e->s_grid), dim3(e->sNT), args, (size_t)e->s_smem, (cudaStream_t)stream));
+    CK(cudaLaunchKernel(e->s_kfn, dim3(grid), dim3(e->sNT), args, (size_t)e->s_smem, (cudaStream_t)stream));
   } else if (!e->wide && !e->prep_fused) {
-    CK(cudaLaunchKernel(e->kfn, dim3(e->grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
+    CK(cudaLaunchKernel(e->kfn, dim3(grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
   } else {
     // prep (thread per robot half), then the step kernel under programmatic dependent launch:
     // its prologue and first wall copies overlap the prep kernel, griddepcontrol.wait orders the rest
-    const unsigned halves = (unsigned)e->cfg.n_worlds * e->cfg.n_robots * ((flags & BRS_STEP_MOVE) ? 2u : 1u);
+    const unsigned halves = (unsigned)n * c.n_robots * ((flags & BRS_STEP_MOVE) ? 2u : 1u);
     CK(cudaLaunchKernel((const void*)brs_prep_kernel, dim3((halves + 255u) / 256u), dim3(256), args, 0, (cudaStream_t)stream));
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(e->wide ? e->w_grid : e->grid);
+    lc.gridDim = dim3(grid);
     lc.blockDim = dim3(e->wide ? e->wNT : e->T);
     lc.dynamicSmemBytes = (size_t)(e->wide ? e->w_smem : e->smem);
     lc.stream = (cudaStream_t)stream;
@@ -836,6 +910,13 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   }
   CK(cudaGetLastError());
   return BRS_OK;
+}
+
+extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
+  if (!(flags & BRS_STEP_ALL)) return BRS_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  return launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream);
 }
 
 extern "C" int brs_step_counted(brs_engine* e, double time_step, unsigned flags, void* stream,
@@ -856,19 +937,94 @@ extern "C" int brs_step_counted(brs_engine* e, double time_step, unsigned flags,
   return BRS_OK;
 }
 
+// The end-to-end step.  The batch is cut into `host_chunks` world ranges: the kernel of range
+// c+1 runs on the caller's stream while the observations of range c drain to the host on the
+// engine's copy stream (one cudaMemcpyAsync per buffer and range); the caller's stream then
+// waits for the last copy, so everything enqueued after this call sees the host buffers filled.
 extern "C" int brs_step_host(brs_engine* e, double time_step, unsigned flags, const double* h_target_vel,
                              double* h_pose, uint8_t* h_stalled, float* h_range, uint8_t* h_camera, float* h_light,
                              float* h_smell, void* stream) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_step_host: null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  const int B = e->cfg.n_worlds, C = std::max(1, std::min(e->host_chunks, B));
+  cudaStream_t st = (cudaStream_t)stream;
+  struct Out { int which; void* host; };
+  const Out outs[] = {{BRS_BUF_POSE, h_pose}, {BRS_BUF_STALLED, h_stalled}, {BRS_BUF_RANGE, h_range},
+                      {BRS_BUF_CAMERA, h_camera}, {BRS_BUF_LIGHT, h_light}, {BRS_BUF_SMELL, h_smell}};
   int rc;
-  if (h_target_vel && (rc = brs_upload(e, BRS_BUF_TARGET_VEL, h_target_vel, 0, -1, stream))) return rc;
-  if ((rc = brs_step(e, time_step, flags, stream))) return rc;
-  if (h_pose && (rc = brs_download(e, BRS_BUF_POSE, h_pose, 0, -1, stream))) return rc;
-  if (h_stalled && (rc = brs_download(e, BRS_BUF_STALLED, h_stalled, 0, -1, stream))) return rc;
-  if (h_range && (rc = brs_download(e, BRS_BUF_RANGE, h_range, 0, -1, stream))) return rc;
-  if (h_camera && (rc = brs_download(e, BRS_BUF_CAMERA, h_camera, 0, -1, stream))) return rc;
-  if (h_light && (rc = brs_download(e, BRS_BUF_LIGHT, h_light, 0, -1, stream))) return rc;
-  if (h_smell && (rc = brs_download(e, BRS_BUF_SMELL, h_smell, 0, -1, stream))) return rc;
+  for (int c = 0; c < C; ++c) {
+    const int first = (int)((long long)B * c / C), n = (int)((long long)B * (c + 1) / C) - first;
+    if (n <= 0) continue;
+    if (h_target_vel) {
+      const size_t sb = e->stride[BRS_BUF_TARGET_VEL];
+      CK(cudaMemcpyAsync((char*)e->buf[BRS_BUF_TARGET_VEL] + sb * first, (const char*)h_target_vel + sb * first, sb * n,
+                         cudaMemcpyHostToDevice, st));
+    }
+    if ((flags & BRS_STEP_ALL) && (rc = launch_range(e, first, n, time_step, flags, stream))) return rc;
+    cudaStream_t cs = C > 1 ? e->copy_stream : st;
+    if (C > 1) {
+      CK(cudaEventRecord(e->ev_chunk[c], st));
+      CK(cudaStreamWaitEvent(cs, e->ev_chunk[c], 0));
+    }
+    for (const Out& o : outs) {
+      const size_t sb = e->stride[o.which];
+      if (o.host && sb)
+        CK(cudaMemcpyAsync((char*)o.host + sb * first, (const char*)cur(e, o.which) + sb * first, sb * n,
+                           cudaMemcpyDeviceToHost, cs));
+    }
+  }
+  if (C > 1) {
+    CK(cudaEventRecord(e->ev_copied, e->copy_stream));
+    CK(cudaStreamWaitEvent(st, e->ev_copied, 0));
+  }
+  return BRS_OK;
+}
+
+// Pinned host memory for brs_step_host, first-touched on the NUMA node of the engine's GPU:
+// the calling thread is moved to the CPUs next to the GPU (sysfs local_cpulist of its PCI
+// function) for the allocation and the touch, then back.  With one process per GPU this keeps
+// each rank's observation traffic on its own socket's memory.
+extern "C" int brs_host_alloc(brs_engine* e, size_t bytes, void** host) {
+  if (!e || !host) return fail(BRS_ERR_INVALID, "brs_host_alloc: null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cpu_set_t old_set, new_set;
+  bool moved = false;
+  CPU_ZERO(&new_set);
+  if (sched_getaffinity(0, sizeof(old_set), &old_set) == 0) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), e->cfg.device) == cudaSuccess) {
+      for (char* q = bus; *q; ++q) *q = (char)tolower(*q);
+      const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+      if (FILE* f = fopen(path.c_str(), "r")) {
+        char line[4096] = {0};
+        if (fgets(line, sizeof(line), f)) {
+          int n_set = 0;
+          for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            const int k = sscanf(tok, "%d-%d", &a, &b);
+            if (k == 1) b = a;
+            if (k >= 1)
+              for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; ++cpu)
+                if (CPU_ISSET(cpu, &old_set)) { CPU_SET(cpu, &new_set); ++n_set; }
+          }
+          moved = n_set > 0 && sched_setaffinity(0, sizeof(new_set), &new_set) == 0;
+        }
+        fclose(f);
+      }
+    }
+  }
+  void* ptr = nullptr;
+  cudaError_t ce = cudaHostAlloc(&ptr, std::max<size_t>(bytes, 16), cudaHostAllocDefault);
+  if (ce == cudaSuccess) memset(ptr, 0, std::max<size_t>(bytes, 16));  // first touch, on the GPU's node
+  if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+  if (ce != cudaSuccess) return fail(BRS_ERR_CUDA, std::string("brs_host_alloc: ") + cudaGetErrorString(ce));
+  *host = ptr;
+  return BRS_OK;
+}
+
+extern "C" int brs_host_free(brs_engine* e, void* host) {
+  if (e) cudaSetDevice(e->cfg.device);
+  if (host) CK(cudaFreeHost(host));
   return BRS_OK;
 }
 

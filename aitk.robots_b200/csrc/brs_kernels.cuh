@@ -169,6 +169,13 @@ struct KParams {
   // search loops ran (table entries that survived the culls x rays, direct-path segments x
   // rays), [1] box-edge-vs-wall tests the collision classifier ran (4 per disc candidate)
   unsigned long long* counters;
+  // the solo path's descriptors (one robot, one camera, one ray group), copied into the kernel
+  // parameters so that the per-world code reads them from the constant bank instead of HBM / L1
+  RobotDev s_robot;
+  CameraDev s_camera;
+  GroupDev s_group;
+  uint32_t s_sky, s_gnd;  // flat sky / ground colours (row 0 of the row tables)
+  int solo_interleave;    // warp gw takes worlds gw, gw + n_warps, ... (else: consecutive ranges)
 };
 
 // per-column paint record
@@ -376,22 +383,74 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // is nearer, starts at bits(1.0f): only hits with t <= 1 (inside the range)
 // win.  Negative or NaN-free by construction (degenerate entries are zero).
 #define BRS_GKEY_INIT 0x3F800000u
+// Two columns per instruction: sm_100a has packed FP32 (PTX fma.rn.f32x2 / mul.rn.f32x2 ->
+// SASS FFMA2 / FMUL2), and ptxas folds a table scalar broadcast to both halves into the
+// operand (R.F32 against R.F32x2.HI_LO), so a pair of columns costs 4 FP instructions per
+// table entry instead of 8.  Each half is the IEEE mul / fma of the scalar form: same bits.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 template <int NR, bool SL1>
 __device__ __forceinline__ void search_group(const float4* __restrict__ tab, int j0, int j1, int g, int SLrt,
                                              const float (&rx)[NR], const float (&ry)[NR], uint32_t (&key)[NR],
                                              int (&idx)[NR]) {
   const int SL = SL1 ? 1 : SLrt;
-#pragma unroll 4
-  for (int j = j0 + (SL1 ? 0 : g); j < j1; j += SL) {
-    const float4 s = tab[j];
+  if constexpr (NR % 2 == 0) {
+    unsigned long long rx2[NR / 2], ry2[NR / 2];
 #pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      const float invt = fmaf(s.x, rx[k], s.y * ry[k]);     // 1/t = m . r
-      const float w = fmaf(rx[k], s.w, -(ry[k] * s.z));     // u/t = r x q
-      // 0 <= w <= invt as one unsigned compare (negative w has the top bit set)
-      if (__float_as_uint(w) <= __float_as_uint(invt) && (int)__float_as_uint(invt) >= (int)key[k]) {
-        key[k] = __float_as_uint(invt);
-        idx[k] = j;
+    for (int k = 0; k < NR / 2; ++k) {
+      rx2[k] = pack2(rx[2 * k], rx[2 * k + 1]);
+      ry2[k] = pack2(ry[2 * k], ry[2 * k + 1]);
+    }
+#pragma unroll 4
+    for (int j = j0 + (SL1 ? 0 : g); j < j1; j += SL) {
+      const float4 s = tab[j];
+      const unsigned long long mx = pack2(s.x, s.x), my = pack2(s.y, s.y), nqx = pack2(-s.z, -s.z), qy = pack2(s.w, s.w);
+#pragma unroll
+      for (int k = 0; k < NR / 2; ++k) {
+        const unsigned long long invt2 = fma2(mx, rx2[k], mul2(my, ry2[k]));   // 1/t = m . r
+        const unsigned long long w2 = fma2(rx2[k], qy, mul2(ry2[k], nqx));     // u/t = r x q
+        float invt[2], w[2];
+        unpack2(invt2, invt[0], invt[1]);
+        unpack2(w2, w[0], w[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          // 0 <= w <= invt as one unsigned compare (negative w has the top bit set)
+          if (__float_as_uint(w[h]) <= __float_as_uint(invt[h]) && (int)__float_as_uint(invt[h]) >= (int)key[2 * k + h]) {
+            key[2 * k + h] = __float_as_uint(invt[h]);
+            idx[2 * k + h] = j;
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int j = j0 + (SL1 ? 0 : g); j < j1; j += SL) {
+      const float4 s = tab[j];
+#pragma unroll
+      for (int k = 0; k < NR; ++k) {
+        const float invt = fmaf(s.x, rx[k], s.y * ry[k]);     // 1/t = m . r
+        const float w = fmaf(rx[k], s.w, -(ry[k] * s.z));     // u/t = r x q
+        // 0 <= w <= invt as one unsigned compare (negative w has the top bit set)
+        if (__float_as_uint(w) <= __float_as_uint(invt) && (int)__float_as_uint(invt) >= (int)key[k]) {
+          key[k] = __float_as_uint(invt);
+          idx[k] = j;
+        }
       }
     }
   }

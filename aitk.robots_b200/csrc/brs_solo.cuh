@@ -35,6 +35,12 @@
 
 namespace brs {
 
+#ifndef BRS_SOLO_TCH
+#define BRS_SOLO_TCH 1  // chunks of 32 walls per TABLE pass (independent chains in flight)
+#endif
+#ifndef BRS_SOLO_CCH
+#define BRS_SOLO_CCH 1  // chunks of 32 walls per COLLIDE pass
+#endif
 #define BRS_SOLO_BATCH 16  // worlds per PREP pass of a warp (two lanes per world)
 #define BRS_SOLO_REC 16    // doubles per world record
 // record (doubles): committed x y a cos sin | proposed x y a cos sin vx vy va | int2 (S, bits of
@@ -98,8 +104,23 @@ __device__ __forceinline__ void solo_prep_half(const KParams& p, const RobotDev&
   }
 }
 
-// wall j of the warp's staged store as the FP32 search segment (x1, y1, ex, ey)
-__device__ __forceinline__ float4 solo_wall(const uint32_t* __restrict__ raw, int SC, int j) {
+// The warp's staged wall store seen from one lane: the four SoA rows at this lane's column, so
+// that wall j0 + lane of chunk j0 is four loads at constant offsets from four registers.
+struct LaneWalls {
+  const uint32_t *x1, *y1, *x2, *y2;
+};
+__device__ __forceinline__ LaneWalls lane_walls(const uint32_t* __restrict__ raw, int SC, int lane) {
+  LaneWalls lw;
+  lw.x1 = raw + lane; lw.y1 = lw.x1 + SC; lw.x2 = lw.y1 + SC; lw.y2 = lw.x2 + SC;
+  return lw;
+}
+// wall j0 + lane as the FP32 search segment (x1, y1, ex, ey)
+__device__ __forceinline__ float4 solo_wall(const LaneWalls& lw, int j0) {
+  const float ax = __uint_as_float(lw.x1[j0]), ay = __uint_as_float(lw.y1[j0]);
+  return make_float4(ax, ay, __uint_as_float(lw.x2[j0]) - ax, __uint_as_float(lw.y2[j0]) - ay);
+}
+// wall j (any lane) the same way
+__device__ __forceinline__ float4 solo_wall_at(const uint32_t* __restrict__ raw, int SC, int j) {
   const float ax = __uint_as_float(raw[j]), ay = __uint_as_float(raw[SC + j]);
   return make_float4(ax, ay, __uint_as_float(raw[2 * SC + j]) - ax, __uint_as_float(raw[3 * SC + j]) - ay);
 }
@@ -107,25 +128,37 @@ __device__ __forceinline__ float4 solo_wall(const uint32_t* __restrict__ raw, in
 // Robot-vs-wall collision of the proposal (collide_commit_tile's COLLIDE for one robot):
 // warp-uniform result.
 __device__ __forceinline__ bool solo_collide(const KParams& p, const RobotDev& rd, const double* __restrict__ r,
-                                             const uint32_t* __restrict__ raw, int SC, int S, int lane) {
+                                             const uint32_t* __restrict__ raw, const LaneWalls& lw, int SC, int S,
+                                             int lane) {
   const float4 cp = *(const float4*)(r + BRS_SR_CPAR);
   bool have_box = false;
   double ax = 0, ay = 0, bx2 = 0, by2 = 0;
   unsigned long long n_cls = 0;
   bool hit = false;
-  for (int j0 = 0; j0 < S; j0 += 32) {
-    const int j = j0 + lane;
-    bool inside = false;
-    if (j < S) {
-      const float4 s = solo_wall(raw, SC, j);
-      const float dx = cp.x - s.x, dy = cp.y - s.y;
-      const float ee = fmaf(s.z, s.z, s.w * s.w);
-      float h = fmaf(dx, s.z, dy * s.w) * rcp_approx(ee);
-      h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
-      const float vx = fmaf(-h, s.z, dx), vy = fmaf(-h, s.w, dy);
-      inside = fmaf(vx, vx, vy * vy) <= cp.z;
+  // four chunks of 32 walls per pass: their disc tests are independent chains the scheduler can
+  // interleave (a warp alone is latency bound); the ballots come after all four
+  for (int jb = 0; jb < S; jb += 32 * BRS_SOLO_CCH) {
+    unsigned inside_bits = 0;
+#pragma unroll
+    for (int c = 0; c < BRS_SOLO_CCH; ++c) {
+      const int j0 = jb + 32 * c;
+      bool inside = false;
+      if (j0 + lane < S) {
+        const float4 s = solo_wall(lw, j0);
+        const float dx = cp.x - s.x, dy = cp.y - s.y;
+        const float ee = fmaf(s.z, s.z, s.w * s.w);
+        float h = fmaf(dx, s.z, dy * s.w) * rcp_approx(ee);
+        h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
+        const float vx = fmaf(-h, s.z, dx), vy = fmaf(-h, s.w, dy);
+        inside = fmaf(vx, vx, vy * vy) <= cp.z;
+      }
+      inside_bits |= (inside ? 1u : 0u) << c;
     }
-    unsigned bal = __ballot_sync(0xffffffffu, inside);
+    if (!__any_sync(0xffffffffu, inside_bits != 0u)) continue;
+#pragma unroll 1
+    for (int c = 0; c < BRS_SOLO_CCH && !hit; ++c) {
+    const int j0 = jb + 32 * c;
+    unsigned bal = __ballot_sync(0xffffffffu, (inside_bits >> c) & 1u);
     while (bal) {  // rare, warp-uniform: lanes 4k+e test box edge e (all octets redundantly)
       const int jj = j0 + __ffs(bal) - 1;
       bal &= bal - 1;
@@ -138,7 +171,7 @@ __device__ __forceinline__ bool solo_collide(const KParams& p, const RobotDev& r
         bx2 = da(px, ds(dm(c, rd.cox[e2]), dm(sgn, rd.coy[e2])));
         by2 = da(py, da(dm(sgn, rd.cox[e2]), dm(c, rd.coy[e2])));
       }
-      const float4 sj = solo_wall(raw, SC, jj);
+      const float4 sj = solo_wall_at(raw, SC, jj);
       const bool maybe = edge_maybe_hits_at((float)r[BRS_SR_PROP], (float)r[BRS_SR_PROP + 1], (float)rd.radius,
                                             p.cull_margin, sj, ax, ay, bx2, by2);
       n_cls += 4;
@@ -149,6 +182,7 @@ __device__ __forceinline__ bool solo_collide(const KParams& p, const RobotDev& r
         if (__ballot_sync(0xffffffffu, h)) hit = true;
       }
       if (hit) break;
+    }
     }
     if (hit) break;
   }
@@ -163,7 +197,8 @@ __device__ __forceinline__ bool solo_collide(const KParams& p, const RobotDev& r
 template <int NR>
 __device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32_t (&rec_rgba)[NR],
                                            const uint32_t (&rec_tb)[NR], const uint32_t* __restrict__ rowsky,
-                                           const uint32_t* __restrict__ rowgnd, bool flat, int lane, int H) {
+                                           const uint32_t* __restrict__ rowgnd, uint32_t sky0, uint32_t gnd0, bool flat,
+                                           int lane, int H) {
   constexpr int Q = 8 * NR, RP = 32 / Q;
   const int q = lane % Q, r0 = lane / Q;
   uint32_t rgba[4];
@@ -180,7 +215,7 @@ __device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32
   }
   uint4* o = out + (size_t)r0 * Q + q;
   if (flat) {
-    const uint32_t sky = rowsky[0], gnd = rowgnd[0];
+    const uint32_t sky = sky0, gnd = gnd0;
     const int t0 = min(min(top[0], top[1]), min(top[2], top[3]));
     const int t1 = max(max(top[0], top[1]), max(top[2], top[3]));
     const int b0 = min(min(bot[0], bot[1]), min(bot[2], bot[3]));
@@ -189,18 +224,44 @@ __device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32
     const uint4 skyq = make_uint4(sky, sky, sky, sky), gndq = make_uint4(gnd, gnd, gnd, gnd);
     const uint4 wallq = make_uint4(rgba[0], rgba[1], rgba[2], rgba[3]);
     int j = r0;
+    // rows of one kind, four stores per loop step (the step's tail is predicated): the loop
+    // bookkeeping is what a row of constant pixels costs
+#define BRS_SOLO_RUN(END, VAL)                                   \
+    {                                                            \
+      const int n = (END - j + RP - 1) / RP;                     \
+      if (n > 0) {                                               \
+        _Pragma("unroll 1") for (int i = 0; i < n; i += 4) {     \
+          __stcs(o + 32 * i, VAL);                               \
+          if (i + 1 < n) __stcs(o + 32 * i + 32, VAL);           \
+          if (i + 2 < n) __stcs(o + 32 * i + 64, VAL);           \
+          if (i + 3 < n) __stcs(o + 32 * i + 96, VAL);           \
+        }                                                        \
+        j += n * RP;                                             \
+        o += 32 * n;                                             \
+      }                                                          \
+    }
+    BRS_SOLO_RUN(e1, skyq)
+    // rows where the quad's walls begin: above every bottom, a pixel is sky or wall
+    {
+      const int e2a = min(e2, e3);
+#pragma unroll 1
+      for (; j < e2a; j += RP, o += 32)
+        __stcs(o, make_uint4(j < top[0] ? sky : rgba[0], j < top[1] ? sky : rgba[1], j < top[2] ? sky : rgba[2],
+                             j < top[3] ? sky : rgba[3]));
+    }
+    // (a wall of the quad ends above where another begins: all three kinds in one row)
 #define BRS_SOLO_PX(k) (j < top[k] ? sky : (j < bot[k] ? rgba[k] : gnd))
 #pragma unroll 1
-    for (; j < e1; j += RP, o += 32) __stcs(o, skyq);
-#pragma unroll 1
     for (; j < e2; j += RP, o += 32) __stcs(o, make_uint4(BRS_SOLO_PX(0), BRS_SOLO_PX(1), BRS_SOLO_PX(2), BRS_SOLO_PX(3)));
-#pragma unroll 1
-    for (; j < e3; j += RP, o += 32) __stcs(o, wallq);
-#pragma unroll 1
-    for (; j < e4; j += RP, o += 32) __stcs(o, make_uint4(BRS_SOLO_PX(0), BRS_SOLO_PX(1), BRS_SOLO_PX(2), BRS_SOLO_PX(3)));
-#pragma unroll 1
-    for (; j < H; j += RP, o += 32) __stcs(o, gndq);
 #undef BRS_SOLO_PX
+    BRS_SOLO_RUN(e3, wallq)
+    // rows where the walls end: below every top, a pixel is wall or ground
+#pragma unroll 1
+    for (; j < e4; j += RP, o += 32)
+      __stcs(o, make_uint4(j < bot[0] ? rgba[0] : gnd, j < bot[1] ? rgba[1] : gnd, j < bot[2] ? rgba[2] : gnd,
+                           j < bot[3] ? rgba[3] : gnd));
+    BRS_SOLO_RUN(H, gndq)
+#undef BRS_SOLO_RUN
   } else {
 #pragma unroll 1
     for (int j = r0; j < H; j += RP, o += 32) {
@@ -231,13 +292,24 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
   uint16_t* const ix = (uint16_t*)(sm + L.idx);
   double* const rec = (double*)(sm + L.rec);
   const uint32_t bar = smem_u32(sm + L.mbar);
+  const LaneWalls lw = lane_walls(raw, SC, lane);
   const bool do_move = p.flags & 1u, do_cam = (p.flags & 4u) && p.n_camera > 0;
   if (!do_move && !do_cam) return;
 
   const unsigned nwarps = gridDim.x * (NT / 32), gw = blockIdx.x * (NT / 32) + wib;
-  const int wbeg = (int)((unsigned long long)p.n_worlds * gw / nwarps);
-  const int wend = (int)((unsigned long long)p.n_worlds * (gw + 1) / nwarps);
-  if (wbeg >= wend) return;
+  // the warp's worlds: world(i) = wbeg + i * wstr, i < cnt.  Interleaved (default): warp gw
+  // takes worlds gw, gw + nwarps, ... so that the pictures being written at any moment form one
+  // dense, sliding window of HBM; contiguous: equal consecutive ranges.
+  int wbeg, wstr, cnt;
+  if (p.solo_interleave) {
+    wbeg = (int)gw; wstr = (int)nwarps;
+    cnt = (int)gw < p.n_worlds ? (p.n_worlds - 1 - (int)gw) / (int)nwarps + 1 : 0;
+  } else {
+    wbeg = (int)((unsigned long long)p.n_worlds * gw / nwarps); wstr = 1;
+    cnt = (int)((unsigned long long)p.n_worlds * (gw + 1) / nwarps) - wbeg;
+  }
+  if (cnt <= 0) return;
+#define BRS_SOLO_WORLD(i) (wbeg + (i) * wstr)
 
   const uint32_t world_bytes = (uint32_t)(5 * SC * 4);
   if (lane == 0) {
@@ -248,9 +320,9 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
   }
   __syncwarp();
 
-  const RobotDev& rd = p.robots[0];
-  const CameraDev& cd = p.cameras[0];
-  const GroupDev& gd = p.groups[0];
+  const RobotDev& rd = p.s_robot;  // (kernel parameters: constant bank, not HBM)
+  const CameraDev& cd = p.s_camera;
+  const GroupDev& gd = p.s_group;
   const int H = p.cam_h;
   const double Hd = (double)cd.height;
   double2 ccs[NR];
@@ -258,18 +330,43 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
   for (int k = 0; k < NR; ++k) ccs[k] = do_cam ? p.cam_cs[lane * NR + k] : make_double2(0.0, 0.0);
   uint32_t parity = 0;
 
-  for (int b0 = wbeg; b0 < wend; b0 += BRS_SOLO_BATCH) {
-    const int nb = min(BRS_SOLO_BATCH, wend - b0);
+  for (int b0 = 0; b0 < cnt; b0 += BRS_SOLO_BATCH) {
+    const int nb = min(BRS_SOLO_BATCH, cnt - b0);
     // ---------------- PREP ----------------------------------------------------------------
     {
       const int wl = lane >> 1;
       const bool prop = lane & 1;
-      if (wl < nb && (!prop || do_move)) solo_prep_half(p, rd, b0 + wl, prop, rec + wl * BRS_SOLO_REC);
+      if (wl < nb && (!prop || do_move)) solo_prep_half(p, rd, BRS_SOLO_WORLD(b0 + wl), prop, rec + wl * BRS_SOLO_REC);
     }
     __syncwarp();
+    // the next batch's robot state, segment counts and world sizes: start them towards L1 now, a
+    // batch of pictures before PREP needs them
+    if (b0 + BRS_SOLO_BATCH < cnt) {
+      if (wstr == 1) {
+        if (lane < 14) {
+          const int wn = BRS_SOLO_WORLD(b0 + BRS_SOLO_BATCH), wlast = BRS_SOLO_WORLD(cnt - 1);
+          const char* a;
+          if (lane < 12) {
+            const double* base = lane < 4 ? p.pose : (lane < 8 ? p.vel : p.tvel);
+            a = (const char*)(base + (size_t)wn * 3) + 128 * (lane & 3);
+            if (a >= (const char*)(base + ((size_t)wlast + 1) * 3)) a = nullptr;
+          } else {
+            a = lane == 12 ? (const char*)(p.seg_count + wn) : (const char*)(p.world_size + 2 * (size_t)wn);
+          }
+          if (a) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        }
+      } else if (b0 + BRS_SOLO_BATCH + (lane >> 1) < cnt) {
+        // scattered worlds: lane pair -> world, its pose / velocity rows and its counts
+        const size_t wn = (size_t)BRS_SOLO_WORLD(b0 + BRS_SOLO_BATCH + (lane >> 1));
+        const char* a = (lane & 1) ? (const char*)(p.vel + wn * 3) : (const char*)(p.pose + wn * 3);
+        const char* b = (lane & 1) ? (const char*)(p.tvel + wn * 3) : (const char*)(p.seg_count + wn);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(b));
+      }
+    }
     unsigned stall_mask = 0;
     for (int k = 0; k < nb; ++k) {
-      const int w = b0 + k;
+      const int w = BRS_SOLO_WORLD(b0 + k);
       const double* r = rec + k * BRS_SOLO_REC;
       const int2 meta = *(const int2*)(r + BRS_SR_META);
       const int S = meta.x;
@@ -277,7 +374,7 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
       parity ^= 1u;
       // ---------------- COLLIDE ------------------------------------------------------------
       bool hit = true;  // !do_move: the committed state stays
-      if (do_move) hit = solo_collide(p, rd, r, raw, SC, S, lane);
+      if (do_move) hit = solo_collide(p, rd, r, raw, lw, SC, S, lane);
       if (hit) stall_mask |= 1u << k;
       uint32_t rec_rgba[NR], rec_tb[NR];
       if (do_cam) {
@@ -300,18 +397,28 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
           gc.oy = (float)oy;
         }
         int cw = 0;
-        for (int j0 = 0; j0 < S; j0 += 32) {
-          const int j = j0 + lane;
-          float4 t;
-          bool keep = false;
-          if (j < S) keep = table_entry(solo_wall(raw, SC, j), gc, t);
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            const int pos = cw + __popc(bal & ((1u << lane) - 1u));
-            tab[pos] = t;
-            ix[pos] = (uint16_t)j;
+        for (int jb = 0; jb < S; jb += 32 * BRS_SOLO_TCH) {
+          // (independent chunks per pass, as in COLLIDE; compaction keeps index order)
+          float4 t[BRS_SOLO_TCH];
+          unsigned keep_bits = 0;
+#pragma unroll
+          for (int c = 0; c < BRS_SOLO_TCH; ++c) {
+            const int j0 = jb + 32 * c;
+            bool keep = false;
+            if (j0 + lane < S) keep = table_entry(solo_wall(lw, j0), gc, t[c]);
+            keep_bits |= (keep ? 1u : 0u) << c;
           }
-          cw += __popc(bal);
+#pragma unroll
+          for (int c = 0; c < BRS_SOLO_TCH; ++c) {
+            const bool keep = (keep_bits >> c) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+              const int pos = cw + __popc(bal & ((1u << lane) - 1u));
+              tab[pos] = t[c];
+              ix[pos] = (uint16_t)(jb + 32 * c + lane);
+            }
+            cw += __popc(bal);
+          }
         }
         __syncwarp();
         if (p.counters && lane == 0) atomicAdd(&p.counters[0], (unsigned long long)cw * (unsigned)p.cam_w);
@@ -333,37 +440,54 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
         }
         search_group<NR, true>(tab, 0, cw, 0, 1, rx, ry, key, idx);
         const double wsize = (double)__int_as_float(meta.y);
+        // Camera._update of the lane's columns (camera_column without other robots), written
+        // branch-free so that the float64 chains of the columns interleave: a column that hit
+        // nothing refines wall 0 and discards the result
+        int jw[NR];
+        double x3[NR], y3[NR], x4[NR], y4[NR];
+        uint32_t wall_rgba[NR];
 #pragma unroll
         for (int c = 0; c < NR; ++c) {
-          // Camera._update of one column (camera_column without other robots)
-          rec_rgba[c] = 0u;
-          rec_tb[c] = 0x7fff0000u;  // nothing hit: colour 0 over every row
-          if (idx[c] >= 0) {
-            const int j = ix[idx[c]];
-            const double x3 = (double)__uint_as_float(raw[j]), y3 = (double)__uint_as_float(raw[SC + j]);
-            const double x4 = (double)__uint_as_float(raw[2 * SC + j]), y4 = (double)__uint_as_float(raw[3 * SC + j]);
-            const double dist = dm(ua64(ox, oy, x2[c], y2[c], x3, y3, x4, y4), cd.max_range);
-            const double dw = dist / wsize;
-            const double s = clamp01(ds(1.0, dm(dw, cd.size_fade)));
-            const double sc = clamp01(ds(1.0, dm(dw, cd.color_fade)));
-            rec_rgba[c] = shade(raw[4 * SC + j], sc);
-            const double high = dm(ds(1.0, s), Hd);
-            const int top = (int)ceil(high / 2.0), bot = (int)ceil(ds(Hd, high / 2.0));
-            rec_tb[c] = (uint32_t)min(max(top, 0), 0x7fff) | ((uint32_t)min(max(bot, 0), 0x7fff) << 16);
-          }
+          jw[c] = idx[c] >= 0 ? (int)ix[idx[c]] : 0;
+          x3[c] = (double)__uint_as_float(raw[jw[c]]);
+          y3[c] = (double)__uint_as_float(raw[SC + jw[c]]);
+          x4[c] = (double)__uint_as_float(raw[2 * SC + jw[c]]);
+          y4[c] = (double)__uint_as_float(raw[3 * SC + jw[c]]);
+          wall_rgba[c] = raw[4 * SC + jw[c]];
+        }
+        double ua[NR], dw[NR];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) ua[c] = ua64(ox, oy, x2[c], y2[c], x3[c], y3[c], x4[c], y4[c]);
+#pragma unroll
+        for (int c = 0; c < NR; ++c) dw[c] = dm(ua[c], cd.max_range) / wsize;
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+          const double s = clamp01(ds(1.0, dm(dw[c], cd.size_fade)));
+          const double sc = clamp01(ds(1.0, dm(dw[c], cd.color_fade)));
+          const uint32_t rgba = shade(wall_rgba[c], sc);
+          const double high = dm(ds(1.0, s), Hd);
+          const int top = (int)ceil(high / 2.0), bot = (int)ceil(ds(Hd, high / 2.0));
+          const bool hitc = idx[c] >= 0;
+          rec_rgba[c] = hitc ? rgba : 0u;
+          // 0 <= top <= bot <= H < 2^15; nothing hit: colour 0 over every row
+          rec_tb[c] = hitc ? ((uint32_t)top | ((uint32_t)bot << 16)) : 0x7fff0000u;
         }
       }
       // every lane is done with this world's walls: request the next world's while the
       // picture is written
       __syncwarp();
-      if (lane == 0 && w + 1 < wend) {
+      if (lane == 0 && b0 + k + 1 < cnt) {
         mbar_expect_tx(bar, world_bytes);
-        tma_bulk_g2s(smem_u32(raw), p.seg + (size_t)(w + 1) * 5 * SC, world_bytes, bar);
+        tma_bulk_g2s(smem_u32(raw), p.seg + (size_t)(w + wstr) * 5 * SC, world_bytes, bar);
       }
       // ---------------- PAINT -----------------------------------------------------------------
+#ifdef BRS_SOLO_NOPAINT  // tuning experiment: everything but the picture stores (one store keeps the records alive)
+      if (do_cam && lane == 0) *(uint2*)(p.cam_out + (size_t)w * (size_t)H * p.cam_w * 4) = make_uint2(rec_rgba[0] ^ rec_rgba[NR - 1], rec_tb[0] ^ rec_tb[NR - 1]);
+#else
       if (do_cam)
         solo_paint<NR>((uint4*)(p.cam_out + (size_t)w * (size_t)H * p.cam_w * 4), rec_rgba, rec_tb, p.row_sky, p.row_gnd,
-                       p.flat_rows != 0, lane, H);
+                       p.s_sky, p.s_gnd, p.flat_rows != 0, lane, H);
+#endif
     }
     // ---------------- COMMIT ------------------------------------------------------------------
     if (do_move) {
@@ -371,7 +495,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
       if (wl < nb) {
         const bool hit = (stall_mask >> wl) & 1u;
         const double* r = rec + wl * BRS_SOLO_REC;
-        const size_t o = (size_t)(b0 + wl) * 3;
+        const int wc = BRS_SOLO_WORLD(b0 + wl);
+        const size_t o = (size_t)wc * 3;
         if (lane & 1) {
           p.vel[o] = hit ? 0.0 : r[BRS_SR_PROP + 5];
           p.vel[o + 1] = hit ? 0.0 : r[BRS_SR_PROP + 6];
@@ -382,12 +507,13 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
             p.pose[o + 1] = r[BRS_SR_PROP + 1];
             p.pose[o + 2] = r[BRS_SR_PROP + 2];
           }
-          p.stalled[b0 + wl] = (uint8_t)(hit ? 1 : 0);
+          p.stalled[wc] = (uint8_t)(hit ? 1 : 0);
         }
       }
     }
     __syncwarp();  // the records are overwritten by the next batch
   }
+#undef BRS_SOLO_WORLD
 }
 
 #endif  // __CUDACC__

@@ -61,6 +61,7 @@ class BatchEngine:
                  ground_grad=(0, 0, 0), light_multiplier=1000.0):
         self._lib = cabi.load()
         self._h = None
+        self._host_allocs = []
         self.scene = scene
         self.device = int(device)
         self.n_worlds = scene.n_worlds
@@ -133,6 +134,9 @@ class BatchEngine:
     # -- lifetime --------------------------------------------------------------
     def close(self):
         if self._h is not None:
+            for ptr in self._host_allocs:
+                self._lib.brs_host_free(self._h, ptr)
+            self._host_allocs = []
             self._lib.brs_destroy(self._h)
             self._h = None
 
@@ -217,6 +221,16 @@ class BatchEngine:
             self._lib.brs_step_host(self._h, float(dt), int(flags), target_vel, pose, stalled, range_, camera, light,
                                     smell, stream)
         )
+
+    def host_buffer(self, shape, dtype):
+        """Pinned host array for step_host(), allocated by the C ABI on the NUMA node of this
+        engine's GPU (brs_host_alloc); freed with the engine."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        cabi.check(self._lib.brs_host_alloc(self._h, n, C.byref(ptr)))
+        self._host_allocs.append(ptr.value)
+        buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def step_counted(self, time_step=None, flags=cabi.STEP_ALL, stream=0):
         """One real step with the executed work counted on the device:

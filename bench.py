@@ -388,9 +388,11 @@ class Bench:
         rb = self.rb
         scene = make_scene(rb, config, B, self.rank * B)
         eng = rb.BatchEngine(scene, device=self.local_rank)
-        flags = rb.STEP_ALL
+        flags = {"all": rb.STEP_ALL, "move": rb.STEP_MOVE, "camera": rb.STEP_CAMERA, "sense": rb.STEP_SENSE,
+                 "move+camera": rb.STEP_MOVE | rb.STEP_CAMERA}[self.args.flags]
         tests_per_step = eng.count_tests(flags, self.sh)
-        assert tests_per_step == scene.tests_per_step(), (tests_per_step, scene.tests_per_step())
+        if flags == rb.STEP_ALL:
+            assert tests_per_step == scene.tests_per_step(), (tests_per_step, scene.tests_per_step())
         total_ms, launch_ms = self.time_steps(eng, flags, steps, warmup, per_launch)
         executed = None
         try:
@@ -414,25 +416,23 @@ class Bench:
         return out, None, None
 
 
-def pinned(torch, shape, dt):
-    return torch.empty(shape, dtype=dt, pin_memory=True)
-
-
 def e2e_measure(bench, eng, scene, steps):
     """The same step through brs_step_host: target velocities host->device, every observation
     device->host, pinned buffers, all inside the timed region."""
     torch, rb = bench.torch, bench.rb
+    import numpy as np
+
     B = eng.n_worlds
-    h_tvel = pinned(torch, (B, eng.n_robots, 3), torch.float64)
+    # pinned host buffers from the C ABI: first-touched on this GPU's NUMA node (brs_host_alloc)
+    hb = lambda shape, dt: torch.from_numpy(eng.host_buffer(shape, dt))  # noqa: E731
+    h_tvel = hb((B, eng.n_robots, 3), np.float64)
     h_tvel.copy_(torch.from_numpy(scene.target_vel))
-    h_pose = pinned(torch, (B, eng.n_robots, 3), torch.float64)
-    h_stalled = pinned(torch, (B, eng.n_robots), torch.uint8)
-    h_range = pinned(torch, (B, max(eng.n_range, 1)), torch.float32)
-    h_cam = pinned(torch, (B, max(eng.n_camera, 1), max(eng.cam_h, 1), max(eng.cam_w, 1), 4), torch.uint8)
-    h_light = pinned(torch, (B, max(eng.n_light, 1)), torch.float32)
-    h_smell = pinned(torch, (B, max(eng.n_smell, 1)), torch.float32)
-    for t in (h_pose, h_stalled, h_range, h_cam, h_light, h_smell):
-        t.zero_()  # first touch on this rank's (GPU-local) NUMA node
+    h_pose = hb((B, eng.n_robots, 3), np.float64)
+    h_stalled = hb((B, eng.n_robots), np.uint8)
+    h_range = hb((B, max(eng.n_range, 1)), np.float32)
+    h_cam = hb((B, max(eng.n_camera, 1), max(eng.cam_h, 1), max(eng.cam_w, 1), 4), np.uint8)
+    h_light = hb((B, max(eng.n_light, 1)), np.float32)
+    h_smell = hb((B, max(eng.n_smell, 1)), np.float32)
     h2d = h_tvel.numel() * 8
     d2h = (h_pose.numel() * 8 + h_stalled.numel() + eng.n_range * B * 4 + eng.n_camera * B * eng.cam_h * eng.cam_w * 4
            + eng.n_light * B * 4 + eng.n_smell * B * 4)
@@ -458,15 +458,21 @@ def e2e_measure(bench, eng, scene, steps):
     e2e_ms = e0.elapsed_time(e1)
     # the host ceiling: the same bytes as ONE plain device->host copy per rank, all ranks at
     # once, no kernel -- what the PCIe links and the host memory system deliver on this box
-    big = h_cam if eng.n_camera else h_pose
-    src = eng.tensor("camera" if eng.n_camera else "pose")
+    big, big_name = (h_cam, "camera") if eng.n_camera else (h_pose, "pose")
+
+    def plain_copy():
+        from aitk_robots_b200 import _cabi as cabi
+        from aitk_robots_b200.engine import _BUF_META
+
+        cabi.check(eng._lib.brs_download(eng._h, _BUF_META[big_name][0], big.data_ptr(), 0, B, bench.sh))
+
     for _ in range(2):
-        big.copy_(src.view(big.shape), non_blocking=True)
+        plain_copy()
     bench.barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record(bench.stream)
     for _ in range(n):
-        big.copy_(src.view(big.shape), non_blocking=True)
+        plain_copy()
     c1.record(bench.stream)
     bench.barrier()
     copy_ms = c0.elapsed_time(c1)
@@ -579,6 +585,8 @@ def main():
                     help="skip the supplementary run at 4x the worlds (shows the launch prologue/tail share)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the other BASELINE.json configurations (config1/3/4 sub-objects of the default line)")
+    ap.add_argument("--flags", default="all", choices=["all", "move", "camera", "sense", "move+camera"],
+                    help="tuning: which parts of World.step the device-timed steps run (the default line always uses all)")
     ap.add_argument("--gather", action="store_true", help="also time the optional NCCL observation all-gather")
     args = ap.parse_args()
     if not args.worlds:

@@ -175,13 +175,23 @@ int brs_step_counted(brs_engine* e, double time_step, unsigned flags, void* stre
 
 /* Same step driven with HOST buffers (the end-to-end path): copies target
  * velocities host->device, steps, and copies every non-NULL observation back
- * device->host, all on `stream`.  h_* should be pinned. */
+ * device->host.  Large batches are cut into world ranges so that the kernel of one range
+ * overlaps the device->host copies of the previous one (an internal copy stream); `stream`
+ * waits for the last copy, so the call is ordered on `stream` like a single operation.
+ * h_* should be pinned (brs_host_alloc).  Stands in for the caller-side loop upstream users
+ * write around World.step: set Robot.move targets, step, read get_distance / take_picture. */
 int brs_step_host(brs_engine* e, double time_step, unsigned flags,
                   const double* h_target_vel, /* [B][R][3] or NULL */
                   double* h_pose,             /* [B][R][3] or NULL */
                   uint8_t* h_stalled,         /* [B][R] or NULL */
                   float* h_range, uint8_t* h_camera, float* h_light, float* h_smell,
                   void* stream);
+
+/* Pinned host memory for brs_step_host, allocated and first-touched on the NUMA node of the
+ * engine's GPU (the calling thread is moved to the GPU's local CPUs for the allocation).
+ * No upstream counterpart: upstream observations are Python objects. */
+int brs_host_alloc(brs_engine* e, size_t bytes, void** host);
+int brs_host_free(brs_engine* e, void* host);
 
 /* Block the calling host thread until `stream` has drained. */
 int brs_synchronize(brs_engine* e, void* stream);

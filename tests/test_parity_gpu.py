@@ -511,16 +511,71 @@ def test_random_scenes_match_the_oracle():
     from hypothesis import given, settings, HealthCheck
     from hypothesis import strategies as st
 
+    counts = {"ran": 0, "unplaceable": 0}
+
     @settings(max_examples=100, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
     @given(st.integers(0, 2 ** 31 - 1))
     def run(seed):
         try:
             scene = _random_scene(seed)
         except RuntimeError:  # could not place the robots in a cluttered draw
+            counts["unplaceable"] += 1
             return
+        counts["ran"] += 1
         parity.compare(scene, n_steps=3)
 
     run()
+    # the draws that could not be placed are counted, not silently passed
+    assert counts["ran"] >= 90 and counts["unplaceable"] <= 10, counts
+
+
+def test_soak_1000_random_scenes():
+    """The round-1 soak as a test: 1000 seeded random scenes (1-6 worlds each, every device
+    mix) x 4 steps against the oracle; the number of unplaceable draws is asserted and hit /
+    no-hit flips (only ever excused by the end-point margin) are counted."""
+    ok, skipped = 0, 0
+    tot = {"worlds": 0, "ranges": 0, "range_hit_flips": 0, "pixels": 0, "pixel_mismatch": 0, "lights": 0, "light_flips": 0}
+    for seed in range(20_000, 21_000):
+        try:
+            scene = _random_scene(seed)
+        except RuntimeError:
+            skipped += 1
+            continue
+        st = parity.compare(scene, n_steps=4)
+        for k in tot:
+            tot[k] += st[k]
+        ok += 1
+    assert ok + skipped == 1000 and skipped <= 50, (ok, skipped)
+    assert tot["worlds"] >= 2000 and tot["ranges"] > 5000 and tot["pixels"] > 1_000_000, tot
+    assert tot["range_hit_flips"] <= 1e-3 * tot["ranges"] and tot["pixel_mismatch"] <= 1e-4 * tot["pixels"], tot
+    print("soak:", ok, "scenes,", skipped, "unplaceable,", tot)
+
+
+@pytest.mark.parametrize("config,n_worlds,steps", [("config2", 4096, 2), ("config3", 65536, 5), ("config4", 131072, 3)])
+def test_full_size_batches_oracle_on_64_random_worlds(config, n_worlds, steps):
+    """BASELINE.json sizes: the whole batch is stepped on the GPU, 64 randomly drawn worlds of
+    it are stepped by the oracle and every output of those worlds is compared."""
+    scene = getattr(rb.scenes, config)(n_worlds=n_worlds)
+    gpu = parity.run_engine(scene, steps)
+    rng = np.random.Generator(np.random.PCG64(99))
+    worlds = sorted(int(i) for i in rng.choice(n_worlds, size=64, replace=False))
+    stats = parity.compare_outputs(scene, gpu, steps, worlds, camera=True)
+    assert stats["worlds"] == 64 and stats["max_pose_err"] < 1e-9
+    assert stats["pixel_mismatch"] <= 0.002 * max(stats["pixels"], 1)
+    assert stats["range_hit_flips"] <= 0.002 * max(stats["ranges"], 1)
+
+
+@pytest.mark.parametrize("S", [10, 30, 100, 300, 1000, 2000])
+def test_config5_every_sweep_cell(S):
+    """All 30 cells of the config 5 sweep (6 wall counts x 5 ray counts): oracle on two worlds
+    of every cell."""
+    B = 8 if S < 1000 else 4
+    base = rb.scenes.config5(n_worlds=B, n_segments=S, n_rays=256)
+    for n in (1, 4, 16, 64, 256):
+        base.robots[0].devices = [rb.RangeSpec(position=(0.0, 0.0), a=360.0 * i / n, max=200.0, width=0.0,
+                                               name="ray%d" % i) for i in range(n)]
+        stats = parity.compare(base, n_steps=2, worlds=(0, B - 1), camera=False)
+        assert stats["ranges"] == 2 * n and stats["max_rel_dist"] < 1e-5, (S, n, stats)
 
 
 def test_very_wide_camera_and_sky_gradient():

@@ -39,3 +39,15 @@ PY
     echo "launches $name rc=$?"
   fi
 done < $SPEC
+# the full default bench line (all sub-objects), as the driver runs it
+if [ -n "${FULL_BENCH:-}" ]; then
+  timeout 900 python bench.py > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "default bench rc=$?"; tail -c 600 $OUT/bench_default.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/bench_default.json").read().strip().splitlines()[-1])
+    print("headline ms=%.4f frac=%.3f e2e=%.4g ceiling=%.1f GB/s launches=%d"%(d["ms_per_step"],d["roofline"]["frac"],d["e2e"]["value"],d["e2e"]["host_ceiling_gbs"],d["gpu_launches"]))
+    for k,v in d.get("configs",{}).items(): print(k, {kk:vv for kk,vv in v.items() if kk in ("ms_per_step","hbm_frac","fp32_frac","fp32_executed_frac","world_steps_per_sec","seconds_for_1000_steps","gpu_seconds_for_1000_steps")})
+except Exception as e: print("default bench parse ERR", e)
+PY
+fi
