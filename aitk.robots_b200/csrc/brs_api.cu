@@ -83,6 +83,11 @@ struct brs_engine {
   int sNT = 128, s_grid = 1, s_smem = 0, s_warps_per_sm = 0, solo_interleave = 1;
   const void* s_kfn = nullptr;
   int s_ctas_per_sm = 1, f_ctas_per_sm = 1, w_ctas_per_sm = 1;
+  // the solo range path (brs_scan_kernel): one robot, every range sensor on one mount, no camera
+  bool scan = false;
+  GroupDev h_scan_group;
+  SoloRay* d_scan_rays = nullptr;
+  int scan_nrays = 0, scan_SL = 1, scan_NRL = 1;
   // brs_step_host: chunked pipeline (kernel of chunk c+1 overlaps the device->host copies of chunk c)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {}, ev_copied = nullptr;
@@ -315,9 +320,35 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       g.group = k;
     }
   }
+  // what a group's rays can reach: longest range (widened) and, when every direction fits an
+  // arc narrower than 180 degrees, the cone of that arc (robot frame, widened by a margin)
+  auto set_reach = [&](GroupDev& g, const std::vector<double>& ang, double range) {
+    const double PI = 3.14159265358979323846;
+    g.range = (float)(range * (1.0 + 1e-4) + 1e-3);
+    g.has_cone = 0;
+    // smallest arc containing all directions: try every direction as the arc's start
+    double best_w = 1e9, best_lo = 0;
+    for (double a0 : ang) {
+      double w = 0;
+      for (double a : ang) {
+        double d = std::fmod(a - a0, 2 * PI);
+        if (d < 0) d += 2 * PI;
+        w = std::fmax(w, d);
+      }
+      if (w < best_w) { best_w = w; best_lo = a0; }
+    }
+    const double margin = 2e-3;
+    if (!ang.empty() && best_w + 2 * margin < PI - 0.02 && !env_int("BRS_NO_CONE", 0)) {
+      const double lo = best_lo - margin, hi = best_lo + best_w + margin, ax = 0.5 * (lo + hi);
+      g.has_cone = 1;
+      g.lo_c = (float)std::cos(lo); g.lo_s = (float)std::sin(lo);
+      g.hi_c = (float)std::cos(hi); g.hi_s = (float)std::sin(hi);
+      g.ax_c = (float)std::cos(ax); g.ax_s = (float)std::sin(ax);
+    }
+    if (env_int("BRS_NO_RANGE_CULL", 0)) g.range = 3.0e18f;
+  };
   // what each group's rays can reach: longest range and the cone of directions (robot frame)
   {
-    const double PI = 3.14159265358979323846;
     for (size_t k = 0; k < groups.size(); ++k) {
       std::vector<double> ang;
       double range = 0;
@@ -340,28 +371,34 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
         if (cdev[i].group == (int)k) g.cam_rays += e->cameras[i].width;
       for (int i = 0; i < cfg->n_range; ++i)
         if (gdev[i].group == (int)k) g.range_rays += gdev[i].n_rays;
-      g.range = (float)(range * (1.0 + 1e-4) + 1e-3);
-      g.has_cone = 0;
-      // smallest arc containing all directions: try every direction as the arc's start
-      double best_w = 1e9, best_lo = 0;
-      for (double a0 : ang) {
-        double w = 0;
-        for (double a : ang) {
-          double d = std::fmod(a - a0, 2 * PI);
-          if (d < 0) d += 2 * PI;
-          w = std::fmax(w, d);
-        }
-        if (w < best_w) { best_w = w; best_lo = a0; }
+      set_reach(g, ang, range);
+    }
+  }
+  // the solo range path's own view: ALL range rays of a lone robot leave one mount (whatever
+  // BRS_GROUP_MIN made of them above) -> one shared-origin group and a flat ray table
+  std::vector<SoloRay> scan_rays;
+  bool scan_shape = R == 1 && cfg->n_camera == 0 && cfg->n_light == 0 && cfg->n_smell == 0 && cfg->n_range >= 1 &&
+                    cfg->seg_cap <= 65532;
+  if (scan_shape) {
+    std::vector<double> ang;
+    double range = 0;
+    for (int i = 0; i < cfg->n_range && scan_shape; ++i) {
+      if (gdev[i].mx != gdev[0].mx || gdev[i].my != gdev[0].my) scan_shape = false;
+      for (int q = 0; q < gdev[i].n_rays; ++q) {
+        SoloRay sr;
+        sr.cr = gdev[i].cr[q]; sr.sr = gdev[i].sr[q]; sr.max = gdev[i].max; sr.sensor = i; sr._pad = 0;
+        scan_rays.push_back(sr);
+        ang.push_back(std::atan2(gdev[i].sr[q], gdev[i].cr[q]));
       }
-      const double margin = 2e-3;
-      if (!ang.empty() && best_w + 2 * margin < PI - 0.02 && !env_int("BRS_NO_CONE", 0)) {
-        const double lo = best_lo - margin, hi = best_lo + best_w + margin, ax = 0.5 * (lo + hi);
-        g.has_cone = 1;
-        g.lo_c = (float)std::cos(lo); g.lo_s = (float)std::sin(lo);
-        g.hi_c = (float)std::cos(hi); g.hi_s = (float)std::sin(hi);
-        g.ax_c = (float)std::cos(ax); g.ax_s = (float)std::sin(ax);
-      }
-      if (env_int("BRS_NO_RANGE_CULL", 0)) g.range = 3.0e18f;
+      range = std::fmax(range, gdev[i].max);
+    }
+    if (scan_rays.size() > 256) scan_shape = false;
+    if (scan_shape) {
+      memset(&e->h_scan_group, 0, sizeof(GroupDev));
+      e->h_scan_group.robot = 0; e->h_scan_group.mx = gdev[0].mx; e->h_scan_group.my = gdev[0].my;
+      e->h_scan_group.cam_rays = 0; e->h_scan_group.range_rays = (int)scan_rays.size();
+      set_reach(e->h_scan_group, ang, range);
+      e->scan_nrays = (int)scan_rays.size();
     }
   }
   std::vector<int> gr_idx, dr_idx;
@@ -392,7 +429,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       (rc = to_device(&e->d_smells, sdev)) || (rc = to_device(&e->d_camcs, camcs)) ||
       (rc = to_device(&e->d_groups, groups)) || (rc = to_device(&e->d_gr_idx, gr_idx)) ||
       (rc = to_device(&e->d_dr_idx, dr_idx)) ||
-      (rc = to_device(&e->d_rowsky, rowsky)) || (rc = to_device(&e->d_rowgnd, rowgnd))) {
+      (rc = to_device(&e->d_rowsky, rowsky)) || (rc = to_device(&e->d_rowgnd, rowgnd)) ||
+      (scan_shape && (rc = to_device(&e->d_scan_rays, scan_rays)))) {
     brs_destroy(e);
     return rc;
   }
@@ -676,6 +714,54 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       }
     }
   }
+  // ---- the solo range path: launch geometry -------------------------------------
+  if (scan_shape && !e->solo) {
+    const int K = e->scan_nrays;
+    int nrl = 1, sl = 1;
+    if (K >= 32) {
+      const int per_lane = (K + 31) / 32;
+      nrl = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 8;
+    } else {
+      sl = 32 / pow2ceil(K);
+    }
+    sl = std::max(1, std::min(32, pow2floor(env_int("BRS_SCAN_SL", sl))));
+    if (sl > 1) nrl = std::max(nrl, (K * sl + 31) / 32 <= 1 ? 1 : (K * sl + 31) / 32 <= 2 ? 2 : (K * sl + 31) / 32 <= 4 ? 4 : 8);
+    e->scan_SL = sl; e->scan_NRL = nrl;
+    const int variant = env_int("BRS_SOLO_CTAS", nrl >= 8 ? 4 : 6);  // (8 rays per lane need > 80 registers)
+    const void* sk = nullptr;
+#define BRS_SCK(CT) (nrl == 1 ? (const void*)brs_scan_kernel<1, 128, CT> : nrl == 2 ? (const void*)brs_scan_kernel<2, 128, CT> : nrl == 4 ? (const void*)brs_scan_kernel<4, 128, CT> : (const void*)brs_scan_kernel<8, 128, CT>)
+    if (variant >= 8) sk = BRS_SCK(8);
+    else if (variant <= 4) sk = BRS_SCK(4);
+    else if (variant == 5) sk = BRS_SCK(5);
+    else sk = BRS_SCK(6);
+#undef BRS_SCK
+    const ScanLayout SL_ = make_scan_layout(cfg->n_range, K, 4);
+    e->sNT = 128;
+    e->s_smem = SL_.total;
+    e->s_kfn = sk;
+    bool ok = (size_t)e->s_smem <= prop.sharedMemPerBlockOptin && nrl * 32 >= K * sl;
+    int snb = 0;
+    if (ok) {
+      ce = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, e->s_smem);
+      if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&snb, sk, e->sNT, e->s_smem);
+      ok = ce == cudaSuccess && snb >= 1;
+      if (!ok) cudaGetLastError();
+    }
+    if (ok) {
+      snb = std::min(snb, env_int("BRS_SOLO_MAX_CTAS", 32));
+      e->s_warps_per_sm = snb * 4;
+      e->s_ctas_per_sm = snb;
+      e->s_grid = std::max(1, std::min((cfg->n_worlds + 3) / 4, snb * e->sm_count));
+      // measured over the 30 cells of the config 5 sweep (profiles/r2): a warp per world wins once
+      // a world has a few hundred ray-wall pairs or walls; tiny worlds (10 walls x 4 rays) keep the
+      // fused kernel, whose tiles fill the lanes of the per-robot phases with many worlds
+      const bool enough_work = (long long)K * cfg->seg_cap >= 256 || cfg->seg_cap >= 256;
+      const bool auto_scan = enough_work && cfg->n_worlds >= env_int("BRS_SOLO_MIN_WORLDS", 4 * e->s_warps_per_sm * e->sm_count);
+      e->scan = env_int("BRS_SOLO", auto_scan ? 1 : 0) != 0;
+      e->solo_interleave = env_int("BRS_SOLO_INTERLEAVE", 1) != 0;
+      if (e->scan) { e->solo = true; e->wide = false; e->prep_fused = false; }  // (solo = "a warp-per-world plan is active")
+    }
+  }
   // ---- brs_step_host pipeline: a copy stream and the events that chain it to the caller's
   e->host_chunks = std::max(1, std::min(8, env_int("BRS_HOST_CHUNKS", cfg->n_worlds >= 8192 ? 4 : 1)));
   ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
@@ -725,6 +811,7 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_rowgnd);
   cudaFree(e->d_ws);
   cudaFree(e->d_counters);
+  cudaFree(e->d_scan_rays);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (int k = 0; k < 8; ++k)
     if (e->ev_chunk[k]) cudaEventDestroy(e->ev_chunk[k]);
@@ -859,6 +946,10 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
   p.s_robot = e->h_robot0; p.s_camera = e->h_camera0; p.s_group = e->h_group0;
   p.s_sky = e->h_sky0; p.s_gnd = e->h_gnd0;
   p.solo_interleave = e->solo_interleave;
+  if (e->scan) {
+    p.s_group = e->h_scan_group;
+    p.s_rays = e->d_scan_rays; p.s_nrays = e->scan_nrays; p.s_SL = e->scan_SL;
+  }
 }
 
 // One World.step over worlds [first, first + n): every buffer has `world` as its leading
@@ -1067,7 +1158,7 @@ extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem
 
 extern "C" int brs_path_info(brs_engine* e, int* wide, int* launches_per_step) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_path_info: null engine");
-  if (wide) *wide = e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
+  if (wide) *wide = e->scan ? 4 : e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
   if (launches_per_step) *launches_per_step = (!e->solo && (e->wide || e->prep_fused)) ? 2 : 1;
   return BRS_OK;
 }
@@ -1078,7 +1169,7 @@ extern "C" int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, 
   if (worlds_per_tile) *worlds_per_tile = e->solo ? 1 : e->wide ? e->wTW : e->TW;
   if (n_tiles) *n_tiles = e->solo ? e->cfg.n_worlds : e->wide ? e->w_tiles : e->n_tiles;
   if (workers) *workers = e->solo ? e->sNT : e->wide ? e->wNT : e->NW;
-  if (cols_per_thread) *cols_per_thread = e->solo ? e->cam_w / 32 : e->NR;
+  if (cols_per_thread) *cols_per_thread = e->scan ? e->scan_NRL : e->solo ? e->cam_w / 32 : e->NR;
   if (n_groups) *n_groups = e->n_group;
   return BRS_OK;
 }

@@ -117,6 +117,7 @@ __host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
   return f;
 }
 
+struct SoloRay;
 struct KParams {
   int n_worlds, n_robots, seg_cap, n_bulbs, grid_w, grid_h;
   int n_range, n_camera, n_light, n_smell, n_group;
@@ -176,6 +177,9 @@ struct KParams {
   GroupDev s_group;
   uint32_t s_sky, s_gnd;  // flat sky / ground colours (row 0 of the row tables)
   int solo_interleave;    // warp gw takes worlds gw, gw + n_warps, ... (else: consecutive ranges)
+  // the solo range path (brs_scan_kernel): every ray of the robot's one mount
+  const struct SoloRay* s_rays;  // [s_nrays]
+  int s_nrays, s_SL;             // rays per world; lanes that share one ray (power of two)
 };
 
 // per-column paint record

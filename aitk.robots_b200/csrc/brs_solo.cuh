@@ -517,4 +517,294 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
 }
 
 #endif  // __CUDACC__
+
+// ==============================================================================
+// The solo RANGE kernel: one warp per world for one robot whose range sensors all sit on one
+// mount (BASELINE.json config 5: 1..256 rays against 10..2000 walls; config 1), no camera.
+//
+// Same skeleton as brs_solo_kernel -- PREP two lanes per world, COLLIDE, shared-origin TABLE,
+// FP32 search, float64 refinement of the winner, COMMIT per batch -- with three differences:
+//   * the walls are not staged: lanes read them straight from L2 / HBM, a wall per lane and
+//     chunk, coalesced (COLLIDE and TABLE each stream the world once; a 2000-wall world would
+//     not fit a warp's share of shared memory, and a 10-wall world does not need staging);
+//   * the table is built and searched in blocks of BRS_SCAN_TB walls, so shared memory per warp
+//     is fixed whatever the wall count; a ray's best hit is carried across blocks;
+//   * rays map to lanes by count: >= 32 rays, NRL rays per lane (two per FFMA2); fewer, SL lanes
+//     share one ray, striding the table, reduced with shuffles (ties to the larger index).
+// A sensor's reading is the minimum over its rays (fan of 3): shared-memory atomicMin on the
+// FP32 bits, then one coalesced store of the world's readings.
+// ==============================================================================
+#define BRS_SCAN_TB 128  // walls per TABLE / search block
+struct __align__(16) SoloRay {
+  double cr, sr;  // cos / sin of (sensor.a - incr_k)
+  double max;
+  int sensor, _pad;
+};
+struct ScanLayout {
+  int tab, idx, rec, sout, per_warp, rays, total;
+};
+__host__ __device__ inline ScanLayout make_scan_layout(int n_range, int n_rays, int warps) {
+  ScanLayout L;
+  int o = 0;
+  L.tab = o; o += BRS_SCAN_TB * 16;
+  L.idx = o; o += BRS_SCAN_TB * 2;
+  L.rec = o; o += BRS_SOLO_BATCH * BRS_SOLO_REC * 8;
+  L.sout = o; o += align_up(n_range * 4, 16);
+  L.per_warp = align_up(o, 128);
+  L.rays = L.per_warp * warps;  // one copy of the ray table per CTA
+  L.total = L.rays + align_up(n_rays * (int)sizeof(SoloRay), 16);
+  return L;
+}
+
+#ifdef __CUDACC__
+// wall j of world w straight from the HBM / L2 wall store: raw end points (exact in float64)
+__device__ __forceinline__ float4 scan_wall_raw(const uint32_t* __restrict__ segw, int SC, int j) {
+  return make_float4(__uint_as_float(__ldg(segw + j)), __uint_as_float(__ldg(segw + SC + j)),
+                     __uint_as_float(__ldg(segw + 2 * SC + j)), __uint_as_float(__ldg(segw + 3 * SC + j)));
+}
+
+template <int NRL, int NT, int MIN_CTAS>
+__global__ void __launch_bounds__(NT, MIN_CTAS) brs_scan_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int SC = p.seg_cap, K = p.s_nrays, SL = p.s_SL;
+  const ScanLayout L = make_scan_layout(p.n_range, K, NT / 32);
+  unsigned char* const sm = smem + (size_t)wib * L.per_warp;
+  float4* const tab = (float4*)(sm + L.tab);
+  uint16_t* const ix = (uint16_t*)(sm + L.idx);
+  double* const rec = (double*)(sm + L.rec);
+  uint32_t* const sout = (uint32_t*)(sm + L.sout);
+  SoloRay* const rays = (SoloRay*)(smem + L.rays);
+  const bool do_move = p.flags & 1u, do_sense = (p.flags & 2u) && K > 0;
+  for (int i = threadIdx.x; i < K; i += NT) rays[i] = p.s_rays[i];
+  __syncthreads();  // (the only CTA-wide barrier: the ray table; the warps are independent from here)
+  if (!do_move && !do_sense) return;
+
+  const unsigned nwarps = gridDim.x * (NT / 32), gw = blockIdx.x * (NT / 32) + wib;
+  int wbeg, wstr, cnt;
+  if (p.solo_interleave) {
+    wbeg = (int)gw; wstr = (int)nwarps;
+    cnt = (int)gw < p.n_worlds ? (p.n_worlds - 1 - (int)gw) / (int)nwarps + 1 : 0;
+  } else {
+    wbeg = (int)((unsigned long long)p.n_worlds * gw / nwarps); wstr = 1;
+    cnt = (int)((unsigned long long)p.n_worlds * (gw + 1) / nwarps) - wbeg;
+  }
+  if (cnt <= 0) return;
+#define BRS_SOLO_WORLD(i) (wbeg + (i) * wstr)
+  const RobotDev& rd = p.s_robot;
+  const GroupDev& gd = p.s_group;
+  // lane -> rays: slot c of this lane is ray (lane / SL) + c * (32 / SL); g = lane % SL strides the table
+  const int g = lane & (SL - 1), rbase = lane / SL, rstep = 32 / SL;
+  const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
+
+  for (int b0 = 0; b0 < cnt; b0 += BRS_SOLO_BATCH) {
+    const int nb = min(BRS_SOLO_BATCH, cnt - b0);
+    // ---------------- PREP ----------------------------------------------------------------
+    {
+      const int wl = lane >> 1;
+      const bool prop = lane & 1;
+      if (wl < nb && (!prop || do_move)) solo_prep_half(p, rd, BRS_SOLO_WORLD(b0 + wl), prop, rec + wl * BRS_SOLO_REC);
+    }
+    __syncwarp();
+    unsigned stall_mask = 0;
+    for (int k = 0; k < nb; ++k) {
+      const int w = BRS_SOLO_WORLD(b0 + k);
+      const double* r = rec + k * BRS_SOLO_REC;
+      const int2 meta = *(const int2*)(r + BRS_SR_META);
+      const int S = meta.x;
+      const uint32_t* const segw = p.seg + (size_t)w * 5 * SC;
+      // the next world's wall rows: start them towards L2 now
+      if (b0 + k + 1 < cnt) {
+        const char* nxt = (const char*)(p.seg + (size_t)(w + wstr) * 5 * SC);
+        for (int o = lane * 128; o < 16 * SC; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+      }
+      // ---------------- COLLIDE ------------------------------------------------------------
+      bool hit = true;  // !do_move: the committed state stays
+      if (do_move) {
+        hit = false;
+        const float4 cp = *(const float4*)(r + BRS_SR_CPAR);
+        bool have_box = false;
+        double ax = 0, ay = 0, bx2 = 0, by2 = 0;
+        unsigned long long n_cls = 0;
+        for (int jb = 0; jb < S && !hit; jb += 128) {
+          // four chunks of 32 walls: all their loads are issued before the first is used (the
+          // walls come from L2 / HBM, a chunk at a time would expose that latency four times)
+          float4 wr4[4];
+          unsigned inside_bits = 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = jb + 32 * c + lane;
+            wr4[c] = j < S ? scan_wall_raw(segw, SC, j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = jb + 32 * c + lane;
+            const float4 wr = wr4[c];
+            const float4 s = make_float4(wr.x, wr.y, wr.z - wr.x, wr.w - wr.y);
+            const float dx = cp.x - s.x, dy = cp.y - s.y;
+            const float ee = fmaf(s.z, s.z, s.w * s.w);
+            float h = fmaf(dx, s.z, dy * s.w) * rcp_approx(ee);
+            h = fminf(fmaxf(h, 0.f), 1.f);  // NaN (zero-length wall) clamps to an end point
+            const float vx = fmaf(-h, s.z, dx), vy = fmaf(-h, s.w, dy);
+            if (j < S && fmaf(vx, vx, vy * vy) <= cp.z) inside_bits |= 1u << c;
+          }
+          if (!__any_sync(0xffffffffu, inside_bits != 0u)) continue;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+          const float4 wr = wr4[c];
+          unsigned bal = __ballot_sync(0xffffffffu, (inside_bits >> c) & 1u);
+          while (bal && !hit) {  // rare, warp-uniform: lanes 4k+e test box edge e
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            if (!have_box) {
+              have_box = true;
+              const int e = lane & 3, e2 = (e + 1) & 3;
+              const double px = r[BRS_SR_PROP], py = r[BRS_SR_PROP + 1], c = r[BRS_SR_PROP + 3], sgn = r[BRS_SR_PROP + 4];
+              ax = da(px, ds(dm(c, rd.cox[e]), dm(sgn, rd.coy[e])));
+              ay = da(py, da(dm(sgn, rd.cox[e]), dm(c, rd.coy[e])));
+              bx2 = da(px, ds(dm(c, rd.cox[e2]), dm(sgn, rd.coy[e2])));
+              by2 = da(py, da(dm(sgn, rd.cox[e2]), dm(c, rd.coy[e2])));
+            }
+            const float x1 = __shfl_sync(0xffffffffu, wr.x, src), y1 = __shfl_sync(0xffffffffu, wr.y, src);
+            const float x2 = __shfl_sync(0xffffffffu, wr.z, src), y2 = __shfl_sync(0xffffffffu, wr.w, src);
+            const float4 sj = make_float4(x1, y1, x2 - x1, y2 - y1);
+            const bool maybe = edge_maybe_hits_at((float)r[BRS_SR_PROP], (float)r[BRS_SR_PROP + 1], (float)rd.radius,
+                                                  p.cull_margin, sj, ax, ay, bx2, by2);
+            n_cls += 4;
+            if (__ballot_sync(0xffffffffu, maybe)) {
+              const bool h = isect64_bool(ax, ay, ds(bx2, ax), ds(by2, ay), (double)x1, (double)y1, (double)x2, (double)y2);
+              if (__ballot_sync(0xffffffffu, h)) hit = true;
+            }
+          }
+          }
+        }
+        if (p.counters && lane == 0 && n_cls) atomicAdd(&p.counters[1], n_cls);
+      }
+      if (hit) stall_mask |= 1u << k;
+      if (do_sense) {
+        const double* f = hit ? r + BRS_SR_POSE : r + BRS_SR_PROP;
+        const double fx = f[0], fy = f[1], fc = f[3], fs = f[4];
+        const double ox = da(fx, ds(dm(fc, gd.mx), dm(fs, gd.my)));
+        const double oy = da(fy, da(dm(fs, gd.mx), dm(fc, gd.my)));
+        GroupCull gc;
+        {
+          const float cf = (float)fc, sf = (float)fs;
+          gc.lo_x = cf * gd.lo_c - sf * gd.lo_s; gc.lo_y = sf * gd.lo_c + cf * gd.lo_s;
+          gc.hi_x = cf * gd.hi_c - sf * gd.hi_s; gc.hi_y = sf * gd.hi_c + cf * gd.hi_s;
+          gc.ax_x = cf * gd.ax_c - sf * gd.ax_s; gc.ax_y = sf * gd.ax_c + cf * gd.ax_s;
+          gc.range2 = gd.range * gd.range;
+          gc.has_cone = gd.has_cone;
+          gc.ox = (float)ox;
+          gc.oy = (float)oy;
+        }
+        // the readings start at each sensor's range
+        for (int i = lane; i < p.n_range; i += 32) sout[i] = __float_as_uint((float)p.ranges[i].max);
+        // this lane's rays, scaled to their range (FP32, search only)
+        float rx[NRL], ry[NRL];
+        uint32_t key[NRL];
+        int widx[NRL];  // winning wall (world index), -1: nothing hit yet
+#pragma unroll
+        for (int c = 0; c < NRL; ++c) {
+          const int ray = rbase + c * rstep;
+          rx[c] = ry[c] = 0.f;  // (a slot past the last ray never hits: 1/t stays 0)
+          if (ray < K) {
+            const SoloRay sr = rays[ray];
+            const double dxu = ds(dm(fc, sr.cr), dm(fs, sr.sr)), dyu = da(dm(fs, sr.cr), dm(fc, sr.sr));
+            const double x2 = da(dm(dxu, sr.max), ox), y2 = da(dm(dyu, sr.max), oy);
+            rx[c] = (float)ds(x2, ox);
+            ry[c] = (float)ds(y2, oy);
+          }
+          key[c] = BRS_GKEY_INIT;
+          widx[c] = -1;
+        }
+        // ---------------- TABLE + SENSE, block by block ---------------------------------------
+        unsigned long long n_exec = 0;
+        for (int jb = 0; jb < S; jb += BRS_SCAN_TB) {
+          int cw = 0;
+          float4 wr4[BRS_SCAN_TB / 32];
+#pragma unroll
+          for (int c = 0; c < BRS_SCAN_TB / 32; ++c) {
+            const int j = jb + 32 * c + lane;
+            wr4[c] = j < S ? scan_wall_raw(segw, SC, j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < BRS_SCAN_TB / 32; ++c) {
+            const int j = jb + 32 * c + lane;
+            float4 t;
+            bool keep = false;
+            if (j < S) {
+              const float4 wr = wr4[c];
+              keep = table_entry(make_float4(wr.x, wr.y, wr.z - wr.x, wr.w - wr.y), gc, t);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+              const int pos = cw + __popc(bal & ((1u << lane) - 1u));
+              tab[pos] = t;
+              ix[pos] = (uint16_t)j;
+            }
+            cw += __popc(bal);
+          }
+          __syncwarp();
+          n_exec += (unsigned long long)cw;
+          int pos[NRL];
+#pragma unroll
+          for (int c = 0; c < NRL; ++c) pos[c] = -1;
+          if (SL == 1)
+            search_group<NRL, true>(tab, 0, cw, 0, 1, rx, ry, key, pos);
+          else
+            search_group<NRL, false>(tab, 0, cw, g, SL, rx, ry, key, pos);
+#pragma unroll
+          for (int c = 0; c < NRL; ++c)
+            if (pos[c] >= 0) widx[c] = ix[pos[c]];  // a nearer hit in this block (ties: the later wall)
+          __syncwarp();  // the next block overwrites the table
+        }
+        if (p.counters && lane == 0) atomicAdd(&p.counters[0], n_exec * (unsigned)K);
+        // ---------------- refinement, readings ------------------------------------------------
+#pragma unroll
+        for (int c = 0; c < NRL; ++c) {
+          if (SL > 1) group_max(key[c], widx[c], SL, gmask);
+          const int ray = rbase + c * rstep;
+          if (g == 0 && ray < K && widx[c] >= 0) {
+            const SoloRay sr = rays[ray];
+            const double dxu = ds(dm(fc, sr.cr), dm(fs, sr.sr)), dyu = da(dm(fs, sr.cr), dm(fc, sr.sr));
+            const double x2 = da(dm(dxu, sr.max), ox), y2 = da(dm(dyu, sr.max), oy);
+            const float4 wr = scan_wall_raw(segw, SC, widx[c]);
+            const double dist = dm(ua64(ox, oy, x2, y2, (double)wr.x, (double)wr.y, (double)wr.z, (double)wr.w), sr.max);
+            const float rd32 = (float)fmin(sr.max, dist);
+            // (+0.0 and -0.0 are the same reading; positive floats order like their bits)
+            atomicMin(&sout[sr.sensor], __float_as_uint(rd32) & 0x7fffffffu);
+          }
+        }
+        __syncwarp();
+        for (int i = lane; i < p.n_range; i += 32) p.range_out[(size_t)w * p.n_range + i] = __uint_as_float(sout[i]);
+        __syncwarp();
+      }
+    }
+    // ---------------- COMMIT ------------------------------------------------------------------
+    if (do_move) {
+      const int wl = lane >> 1;
+      if (wl < nb) {
+        const bool hit = (stall_mask >> wl) & 1u;
+        const double* r = rec + wl * BRS_SOLO_REC;
+        const int wc = BRS_SOLO_WORLD(b0 + wl);
+        const size_t o = (size_t)wc * 3;
+        if (lane & 1) {
+          p.vel[o] = hit ? 0.0 : r[BRS_SR_PROP + 5];
+          p.vel[o + 1] = hit ? 0.0 : r[BRS_SR_PROP + 6];
+          p.vel[o + 2] = hit ? 0.0 : r[BRS_SR_PROP + 7];
+        } else {
+          if (!hit) {
+            p.pose[o] = r[BRS_SR_PROP];
+            p.pose[o + 1] = r[BRS_SR_PROP + 1];
+            p.pose[o + 2] = r[BRS_SR_PROP + 2];
+          }
+          p.stalled[wc] = (uint8_t)(hit ? 1 : 0);
+        }
+      }
+    }
+    __syncwarp();  // the records are overwritten by the next batch
+  }
+#undef BRS_SOLO_WORLD
+}
+#endif  // __CUDACC__
 }  // namespace brs

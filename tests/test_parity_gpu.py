@@ -344,6 +344,61 @@ def test_solo_path_sky_gradient():
         orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD = old
 
 
+def _range_fan_scene(n_worlds, n_segments, n_sensors, width, seed=3):
+    """config 5 with fans: every sensor casts 3 rays when width != 0."""
+    scene = rb.scenes.config5(n_worlds=n_worlds, n_segments=n_segments, n_rays=n_sensors, seed=seed)
+    scene.robots[0].devices = [rb.RangeSpec(position=(1.0, 0.5), a=360.0 * i / n_sensors, max=150.0 + i, width=width,
+                                            name="ray%d" % i) for i in range(n_sensors)]
+    return scene
+
+
+@pytest.mark.parametrize("S,rays", [(12, 1), (12, 7), (100, 16), (100, 64), (300, 4), (300, 256), (1000, 33), (2000, 2)])
+def test_scan_path_bit_identical_and_matches_the_oracle(S, rays):
+    """The solo range path (one warp per world, walls streamed, table in blocks; brs_scan_kernel)
+    against the fused kernel searching the same shared-origin table (BRS_GROUP_MIN=1), bit for
+    bit, and against the oracle; ragged / empty worlds and robots driven into walls included."""
+    B = 37 if S < 1000 else 9
+    scene = rb.scenes.config5(n_worlds=B, n_segments=S, n_rays=rays)
+    scene.seg_count[1] = 0
+    scene.seg_count[2] = min(S, 5)
+    scene.target_vel[:, :, 0] = np.linspace(-2.0, 2.0, B)[:, None]
+
+    def solo():
+        eng = rb.BatchEngine(scene)
+        assert eng.launch_info()["path"].startswith("solo range"), eng.launch_info()
+        eng.close()
+        return parity.run_engine(scene, 6)
+
+    a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0", "BRS_GROUP_MIN": "1"}, lambda: parity.run_engine(scene, 6))
+    for env in ({"BRS_SOLO": "1"}, {"BRS_SOLO": "1", "BRS_SOLO_INTERLEAVE": "0", "BRS_NO_CONE": "1"},
+                {"BRS_SOLO": "1", "BRS_SCAN_SL": "1" if rays > 8 else "4", "BRS_SOLO_CTAS": "8"}):
+        b = _with_env(env, solo)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, env)
+    stats = parity.compare_outputs(scene, b, 6, range(0, B, 4), camera=False)
+    assert stats["max_rel_dist"] < 1e-5 and stats["max_pose_err"] < 1e-9
+
+
+def test_scan_path_fans_and_config1():
+    """Fans of three rays per sensor (the reading is the minimum over the fan), an off-centre
+    mount, and config 1 (one sensor, one ray) on the solo range path."""
+    for scene in (_range_fan_scene(21, 40, 5, 30.0), _range_fan_scene(21, 200, 40, 10.0),
+                  rb.scenes.config1(n_worlds=50)):
+        a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0", "BRS_GROUP_MIN": "1"}, lambda: parity.run_engine(scene, 5))
+
+        def solo():
+            eng = rb.BatchEngine(scene)
+            assert eng.launch_info()["path"].startswith("solo range"), eng.launch_info()
+            eng.close()
+            return parity.run_engine(scene, 5)
+
+        b = _with_env({"BRS_SOLO": "1"}, solo)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        stats = parity.compare_outputs(scene, b, 5, range(scene.n_worlds), camera=False)
+        assert stats["max_rel_dist"] < 1e-5
+
+
 def test_wide_fov_camera_has_no_cone():
     """A 200-degree camera cannot use the cone cull; results still match the oracle."""
     scene = rb.scenes.config2(n_worlds=8, cam_w=64, cam_h=32)

@@ -21,6 +21,7 @@ ap.add_argument("--out", default="gpurun_out/sweep_config5.json")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--segments", default="10,30,100,300,1000,2000")
 ap.add_argument("--rays", default="1,4,16,64,256")
+ap.add_argument("--paths", default="auto", help="comma list of auto,fused,solo: launch plans to time per cell")
 args = ap.parse_args()
 
 peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -36,26 +37,31 @@ for S in [int(v) for v in args.segments.split(",")]:
     for n in [int(v) for v in args.rays.split(",")]:
         base.robots[0].devices = [rb.RangeSpec(position=(0.0, 0.0), a=360.0 * i / n, max=200.0, width=0.0,
                                                name="ray%d" % i) for i in range(n)]
-        eng = rb.BatchEngine(base)
-        tests = eng.count_tests()
-        for _ in range(2):
-            eng.step(stream=stream.cuda_stream)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            eng.step(stream=stream.cuda_stream)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        alg_bytes = B * (20 * eng.seg_cap + 12 + 72 + 48 + 1 + 4 * n)
-        row = {"segments": S, "rays": n, "worlds": B, "ms_per_step": ms, "world_steps_per_sec": B / (ms * 1e-3),
-               "tests_per_sec": tests / (ms * 1e-3), "fp32_frac": tests * 13 / (ms * 1e-3) / 1e12 / ffma,
-               "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "launch": eng.launch_info()}
-        rows.append(row)
-        print("S=%5d rays=%4d worlds=%6d ms=%8.4f tests/s=%.3g fp32=%.3f hbm=%.3f tw=%d workers=%d groups=%d" % (
-            S, n, B, ms, row["tests_per_sec"], row["fp32_frac"], row["hbm_frac"], row["launch"]["worlds_per_tile"],
-            row["launch"]["workers"], row["launch"]["ray_groups"]), flush=True)
-        eng.close()
+        for path in args.paths.split(","):
+            if path == "auto":
+                os.environ.pop("BRS_SOLO", None)
+            else:
+                os.environ["BRS_SOLO"] = "1" if path == "solo" else "0"
+            eng = rb.BatchEngine(base)
+            tests = eng.count_tests()
+            for _ in range(2):
+                eng.step(stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                eng.step(stream=stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            alg_bytes = B * (20 * eng.seg_cap + 12 + 72 + 48 + 1 + 4 * n)
+            row = {"segments": S, "rays": n, "worlds": B, "path_requested": path, "ms_per_step": ms,
+                   "world_steps_per_sec": B / (ms * 1e-3),
+                   "tests_per_sec": tests / (ms * 1e-3), "fp32_frac": tests * 13 / (ms * 1e-3) / 1e12 / ffma,
+                   "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "launch": eng.launch_info()}
+            rows.append(row)
+            print("S=%5d rays=%4d worlds=%6d %-5s ms=%8.4f tests/s=%.3g fp32=%.3f hbm=%.3f | %s" % (
+                S, n, B, path, ms, row["tests_per_sec"], row["fp32_frac"], row["hbm_frac"], row["launch"]["path"][:10]), flush=True)
+            eng.close()
     print("  (scene generation %.1f s)" % gen_s, flush=True)
 json.dump({"ffma_peak_tflops": ffma, "hbm_peak_gbs": hbm_peak, "cells": rows}, open(args.out, "w"), indent=1)
