@@ -127,6 +127,7 @@ SYMBOLS = [
     ("brs_upload", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     ("brs_download", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     ("brs_step", C.c_int, [_P, C.c_double, C.c_uint, _P]),
+    ("brs_set_noise", C.c_int, [_P, C.c_ulonglong, C.c_uint, C.c_double, C.c_double]),
     ("brs_step_counted", C.c_int, [_P, C.c_double, C.c_uint, _P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     ("brs_step_host", C.c_int, [_P, C.c_double, C.c_uint, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("brs_host_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -92,6 +92,9 @@ struct brs_engine {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {}, ev_copied = nullptr;
   int host_chunks = 4;
+  // seeded sensor noise (brs_set_noise); the step counter advances once per sensing step
+  NoiseParams noise = {};
+  unsigned long long noise_step = 0;
   // kernel parameters cached per step-flags value (everything but dt and the rebindable outputs is fixed at create)
   KParams kp_cache;
   unsigned kp_flags = 0xffffffffu;
@@ -882,6 +885,9 @@ static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned fl
   p.light_out = (float*)cur(e, BRS_BUF_LIGHT);
   p.smell_out = (float*)cur(e, BRS_BUF_SMELL);
   p.counters = e->counting ? e->d_counters : nullptr;
+  p.noise = e->noise;
+  p.noise.step_lo = (uint32_t)(e->noise_step & 0xffffffffull);
+  p.noise.step_hi = (uint32_t)(e->noise_step >> 32);
 }
 static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide) {
   const brs_config& c = e->cfg;
@@ -968,6 +974,7 @@ static int launch_range(brs_engine* e, int first, int n, double time_step, unsig
     p.light_out += f * c.n_light; p.smell_out += f * c.n_smell;
     if (p.wsg) p.wsg += f * R * BRS_WS_STRIDE;
     p.n_worlds = n;
+    p.noise.world0 += (uint32_t)first;
     p.n_tiles = (n + p.TW - 1) / p.TW;
     if (e->solo) {
       const int wpc = e->sNT / 32;
@@ -1007,7 +1014,26 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
   if (!(flags & BRS_STEP_ALL)) return BRS_OK;
   CK(cudaSetDevice(e->cfg.device));
-  return launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream);
+  const int rc = launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream);
+  if (flags & BRS_STEP_SENSE) ++e->noise_step;
+  return rc;
+}
+
+// Seeded sensor noise.  Off by default (the parity contract of BASELINE.json is stated with
+// noise disabled); a (seed, world, sensor, step) -> N(0,1) map that no launch detail can change.
+extern "C" int brs_set_noise(brs_engine* e, unsigned long long seed, unsigned first_world, double range_std,
+                             double light_rel_std) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_set_noise: null engine");
+  if (!(range_std >= 0) || !(light_rel_std >= 0)) return fail(BRS_ERR_INVALID, "brs_set_noise: negative standard deviation");
+  memset(&e->noise, 0, sizeof(e->noise));
+  e->noise.on = (range_std > 0 || light_rel_std > 0) ? 1u : 0u;
+  e->noise.k0 = (uint32_t)(seed & 0xffffffffull);
+  e->noise.k1 = (uint32_t)(seed >> 32);
+  e->noise.world0 = first_world;
+  e->noise.range_std = (float)range_std;
+  e->noise.light_rel_std = (float)light_rel_std;
+  e->noise_step = 0;
+  return BRS_OK;
 }
 
 extern "C" int brs_step_counted(brs_engine* e, double time_step, unsigned flags, void* stream,
@@ -1068,6 +1094,7 @@ extern "C" int brs_step_host(brs_engine* e, double time_step, unsigned flags, co
     CK(cudaEventRecord(e->ev_copied, e->copy_stream));
     CK(cudaStreamWaitEvent(st, e->ev_copied, 0));
   }
+  if (flags & BRS_STEP_SENSE) ++e->noise_step;
   return BRS_OK;
 }
 

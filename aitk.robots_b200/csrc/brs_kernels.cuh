@@ -56,7 +56,7 @@
 #endif
 
 #ifndef BRS_PAINT_ZONES
-#define BRS_PAINT_ZONES 1  // constant-quad fast rows in PAINT (0: per-pixel compare / select on every row)
+#define BRS_PAINT_ZONES 0  // 1: constant-quad fast rows in the fused PAINT (measured SLOWER on configs 2 and 4, profiles/r2: kept off)
 #endif
 
 namespace brs {
@@ -118,6 +118,15 @@ __host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
 }
 
 struct SoloRay;
+// Seeded sensor noise (off unless brs_set_noise enabled it): one Philox4x32-10 block per
+// (world, sensor, step) -- counter = (global world index, kind << 24 | sensor, step lo, step hi),
+// key = the 64-bit seed -- so a reading's noise depends on nothing but those four numbers:
+// not on the launch plan, the tiling, the shard a world lives in or the order of execution.
+struct NoiseParams {
+  uint32_t on, k0, k1, step_lo, step_hi, world0;
+  float range_std;      // RangeSensor: reading += range_std * N(0,1), clamped to [0, max]
+  float light_rel_std;  // LightSensor: value *= 1 + light_rel_std * N(0,1), clamped at 0
+};
 struct KParams {
   int n_worlds, n_robots, seg_cap, n_bulbs, grid_w, grid_h;
   int n_range, n_camera, n_light, n_smell, n_group;
@@ -177,6 +186,7 @@ struct KParams {
   GroupDev s_group;
   uint32_t s_sky, s_gnd;  // flat sky / ground colours (row 0 of the row tables)
   int solo_interleave;    // warp gw takes worlds gw, gw + n_warps, ... (else: consecutive ranges)
+  NoiseParams noise;
   // the solo range path (brs_scan_kernel): every ray of the robot's one mount
   const struct SoloRay* s_rays;  // [s_nrays]
   int s_nrays, s_SL;             // rays per world; lanes that share one ray (power of two)
@@ -376,6 +386,40 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// ---- seeded sensor noise: Philox4x32-10 (Salmon et al., SC'11), Box-Muller -----------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+#define BRS_NOISE_RANGE 1u
+#define BRS_NOISE_LIGHT 2u
+// N(0,1) of (world w of this launch, sensor kind / index, this step)
+__device__ __forceinline__ float noise_normal(const KParams& p, int w, uint32_t kind, uint32_t index) {
+  uint32_t x[4];
+  philox4x32_10(p.noise.world0 + (uint32_t)w, (kind << 24) | index, p.noise.step_lo, p.noise.step_hi, p.noise.k0, p.noise.k1, x);
+  const float u1 = ((float)(x[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1), 24 bits
+  const float u2 = ((float)(x[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+__device__ __forceinline__ float range_reading(const KParams& p, int w, int si, float v, float vmax) {
+  if (p.noise.on && p.noise.range_std != 0.f)
+    v = fminf(fmaxf(v + p.noise.range_std * noise_normal(p, w, BRS_NOISE_RANGE, (uint32_t)si), 0.f), vmax);
+  return v;
+}
+__device__ __forceinline__ float light_reading(const KParams& p, int w, int li, float v) {
+  if (p.noise.on && p.noise.light_rel_std != 0.f)
+    v = fmaxf(v * (1.f + p.noise.light_rel_std * noise_normal(p, w, BRS_NOISE_LIGHT, (uint32_t)li)), 0.f);
+  return v;
 }
 
 // ---- FP32 nearest-hit searches ------------------------------------------------
@@ -962,7 +1006,7 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
       // (upstream stores reading = d / max and returns reading * max: the float32
       //  observation cannot see that round trip)
       if (g == 0) {
-        p.range_out[(size_t)w * p.n_range + si] = (float)best;
+        p.range_out[(size_t)w * p.n_range + si] = range_reading(p, w, si, (float)best, (float)sd.max);
         if (p.counters) atomicAdd(&p.counters[0], (unsigned long long)sd.n_rays * (nseg - 4));
       }
     }
@@ -1003,7 +1047,7 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
         if (idx < 0 && dist > 0.0 && br != 0.0) value = da(value, dm(br, p.light_mult) / dm(dist, dist));
       }
       if (g == 0) {
-        p.light_out[(size_t)w * p.n_light + li] = (float)value;
+        p.light_out[(size_t)w * p.n_light + li] = light_reading(p, w, li, (float)value);
         if (p.counters) atomicAdd(&p.counters[0], (unsigned long long)p.n_bulbs * (nseg - 4));
       }
     }
@@ -1533,7 +1577,7 @@ __device__ __forceinline__ void sense_paint_tile(const KParams& p, const int tid
               if (SL > 1) group_max(key[0], idx[0], SL, gmask);
               if (g == 0 && idx[0] >= 0) best = fmin(best, refine64(raw, SC, S, ws, gidx[(size_t)pg * nvis + idx[0]], O.x, O.y, x2, y2, sd.max));
             }
-            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = (float)best;
+            if (g == 0) p.range_out[(size_t)w * p.n_range + si] = range_reading(p, w, si, (float)best, (float)sd.max);
           }
         }
       }

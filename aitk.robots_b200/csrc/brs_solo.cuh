@@ -776,7 +776,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_scan_kernel(const __grid_con
           }
         }
         __syncwarp();
-        for (int i = lane; i < p.n_range; i += 32) p.range_out[(size_t)w * p.n_range + i] = __uint_as_float(sout[i]);
+        for (int i = lane; i < p.n_range; i += 32)
+          p.range_out[(size_t)w * p.n_range + i] = range_reading(p, w, i, __uint_as_float(sout[i]), (float)p.ranges[i].max);
         __syncwarp();
       }
     }

@@ -232,6 +232,11 @@ class BatchEngine:
         buf = (C.c_char * max(n, 1)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def set_noise(self, seed, range_std=0.0, light_rel_std=0.0, first_world=0):
+        """Seeded sensor noise (off by default): Philox4x32-10 keyed by `seed`, one sample per
+        (first_world + world, sensor, step); see include/brs.h brs_set_noise."""
+        cabi.check(self._lib.brs_set_noise(self._h, int(seed), int(first_world), float(range_std), float(light_rel_std)))
+
     def step_counted(self, time_step=None, flags=cabi.STEP_ALL, stream=0):
         """One real step with the executed work counted on the device:
         (ray-segment tests the search loops ran, box-edge tests the collision classifier ran)."""

@@ -272,6 +272,7 @@ class World:
         self._sensed = False
         self._state = {}
         self._obs = {}
+        self._noise = None  # (range_std, light_rel_std): seeded sensor noise, see set_sensor_noise
         self._boundary_wall = bool(boundary_wall)
         self._boundary_color = to_rgba(boundary_wall_color)
         if boundary_wall:
@@ -346,6 +347,29 @@ class World:
 
         return BatchEngine(self.to_scene(copies), device=self.device if device is None else device)
 
+    # -- robots as a sequence (upstream: ``world[0]``, ``for robot in world``) ------------
+    def __iter__(self):
+        return iter(self._robots)
+
+    def __len__(self):
+        return len(self._robots)
+
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            for r in self._robots:
+                if r.name == item:
+                    return r
+            raise KeyError(item)
+        return self._robots[item]
+
+    def set_sensor_noise(self, range_std=0.0, light_rel_std=0.0):
+        """Seeded sensor noise, keyed by the world's ``seed`` (upstream: ``World(seed=...)`` makes
+        noisy experiments reproducible).  Gaussian: range readings += range_std * N(0,1) clamped
+        to [0, max]; light values *= 1 + light_rel_std * N(0,1).  (0, 0) switches it off."""
+        self._noise = (float(range_std), float(light_rel_std)) if (range_std or light_rel_std) else None
+        if self._engine is not None:
+            self._engine.set_noise(int(self.seed), *(self._noise or (0.0, 0.0)))
+
     # -- engine plumbing -----------------------------------------------------------
     def _build(self):
         """(Re)create the engine after a structural change (walls, bulbs, devices, robots).
@@ -363,6 +387,8 @@ class World:
                 d._index = idx[type(d)]
                 idx[type(d)] += 1
         self._engine = BatchEngine(self.to_scene(1), device=self.device)
+        if self._noise is not None:
+            self._engine.set_noise(int(self.seed), *self._noise)
         if carry is not None:
             n = min(carry[0].shape[1], len(self._robots))
             vel = np.zeros((1, len(self._robots), 3), dtype=np.float64)

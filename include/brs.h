@@ -164,6 +164,16 @@ int brs_download(brs_engine* e, int which, void* host, int first_world, int n_wo
  * see that round trip). */
 int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
 
+/* Seeded sensor noise (upstream: World(seed=...) seeds the sensors' noise; its model is not
+ * in the mounted tree, this one is the engine's own and is mirrored by the oracle's
+ * Switches.SENSOR_NOISE).  Off until called with a non-zero deviation.  Every sample is
+ * Philox4x32-10(counter = (first_world + world, kind << 24 | sensor, step), key = seed) ->
+ * Box-Muller N(0,1): RangeSensor reading += range_std * z, clamped to [0, max]; LightSensor
+ * value *= 1 + light_rel_std * z, clamped at 0.  `first_world`: global index of this engine's
+ * world 0 (a multi-GPU shard passes its offset, so noise does not depend on the sharding).
+ * The step counter restarts at 0 and advances once per brs_step / brs_step_host that senses. */
+int brs_set_noise(brs_engine* e, unsigned long long seed, unsigned first_world, double range_std, double light_rel_std);
+
 /* brs_step with the EXECUTED work counted on the device (for the roofline report; the step
  * is a real one, state advances): *ray_tests = ray-segment tests the search loops ran (table
  * entries that survived the range / cone culls x rays, plus direct-path segments x rays),

@@ -71,9 +71,44 @@ class Switches:
     MOVE_ROUND_DIGITS = None                 # Robot.move rounds its targets to this many digits (None: no rounding)
     CAMERA_DEFAULT_FOV = 60                  # degrees
     CAMERA_DEFAULT_SIZE = (64, 32)
+    # Seeded sensor noise.  None = off (BASELINE.json states parity with noise disabled).  Else a
+    # dict(seed=int, range_std=float, light_rel_std=float): the ENGINE'S OWN model (upstream's is
+    # not in the mounted tree), restated here so that the CUDA noise has a checker -- one
+    # Philox4x32-10 block per (world, sensor, step), Box-Muller; see include/brs.h brs_set_noise.
+    SENSOR_NOISE = None
 
 
 SW = Switches
+
+
+# ----------------------------------------------------------------------------
+# Seeded noise: Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy
+# as 1, 2, 3", SC'11; known-answer vectors of the Random123 distribution in tests/test_oracle.py)
+# ----------------------------------------------------------------------------
+NOISE_RANGE, NOISE_LIGHT = 1, 2
+
+
+def philox4x32_10(counter, key):
+    """counter: 4 x uint32, key: 2 x uint32 -> 4 x uint32."""
+    c0, c1, c2, c3 = (int(v) & 0xFFFFFFFF for v in counter)
+    k0, k1 = (int(v) & 0xFFFFFFFF for v in key)
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        hi0, lo0 = p0 >> 32, p0 & 0xFFFFFFFF
+        hi1, lo1 = p1 >> 32, p1 & 0xFFFFFFFF
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return [c0, c1, c2, c3]
+
+
+def noise_normal(seed, world, kind, index, step):
+    """N(0,1) of one (world, sensor kind / index, step): the engine's counter layout."""
+    x = philox4x32_10([world, (kind << 24) | index, step & 0xFFFFFFFF, step >> 32], [seed & 0xFFFFFFFF, seed >> 32])
+    u1 = ((x[0] >> 8) + 0.5) / 16777216.0
+    u2 = ((x[1] >> 8) + 0.5) / 16777216.0
+    return math.sqrt(-2.0 * math.log(u1)) * math.cos(2.0 * math.pi * u2)
 
 
 # ----------------------------------------------------------------------------
@@ -283,6 +318,11 @@ class RangeSensor(_Device):
                 # closest hit is last (list is sorted furthest first)
                 if hits[-1].distance < self.get_reading() * self.max:
                     self.set_reading(hits[-1].distance / self.max)
+        if SW.SENSOR_NOISE and SW.SENSOR_NOISE.get("range_std"):
+            world = self.robot.world
+            z = noise_normal(SW.SENSOR_NOISE["seed"], world.noise_world_index, NOISE_RANGE, self.noise_index, world.noise_step)
+            d = min(max(self.distance + SW.SENSOR_NOISE["range_std"] * z, 0.0), self.max)
+            self.reading, self.distance = d / self.max, d
 
 
 class Camera(_Device):
@@ -414,6 +454,10 @@ class LightSensor(_Device):
             hits = self.robot.cast_ray(p[0], p[1], angle, dist)
             if len(hits) == 0 and dist > 0:
                 self.value += bulb.brightness * SW.LIGHT_MULTIPLIER / (dist ** 2)
+        if SW.SENSOR_NOISE and SW.SENSOR_NOISE.get("light_rel_std"):
+            world = self.robot.world
+            z = noise_normal(SW.SENSOR_NOISE["seed"], world.noise_world_index, NOISE_LIGHT, self.noise_index, world.noise_step)
+            self.value = max(self.value * (1.0 + SW.SENSOR_NOISE["light_rel_std"] * z), 0.0)
 
 
 class SmellSensor(_Device):
@@ -716,6 +760,7 @@ class World:
                 robot.step(time_step)
                 robot.update()
             self.time = round(self.time + time_step, 10)
+        self.noise_step = getattr(self, "noise_step", 0) + 1  # (one noise block per sensor and sensing step)
 
     def update(self):
         for robot in self._robots:
@@ -735,6 +780,7 @@ def assert_default_switches():
     assert SW.MOTION_DT_ON_VY_ONLY and SW.VELOCITY_RAMP and SW.STALL_ZEROES_VELOCITY
     assert SW.MOVE_ALL_THEN_SENSE and SW.RANGE_FAN_INCLUSIVE
     assert SW.LIGHT_MULTIPLIER == 1000.0 and not SW.SMELL_WALLS_BLOCK
+    assert SW.SENSOR_NOISE is None, "parity is stated with sensor noise disabled"
     # facade constants: the product's FacadeDefaults must carry the same values
     from aitk_robots_b200.world import FacadeDefaults as FD
 

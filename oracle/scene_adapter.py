@@ -57,6 +57,8 @@ def build_world(scene, i, mod=None):
             world.time_step = scene.time_step
     else:
         world = mod.World(w, h, boundary_wall=False, time_step=scene.time_step)
+    if not real:
+        world.noise_world_index, world.noise_step = i, 0
     Color = getattr(mod, "Color", None)
     if Color is None and real:
         try:
@@ -112,6 +114,8 @@ def build_world(scene, i, mod=None):
             else:
                 dev = mod.SmellSensor(position=d.position, name=d.name)
             robot.add_device(dev)
+            if not real:
+                dev.noise_index = len(devs[kind])  # index among the world's sensors of this kind, as in the engine
             devs[kind].append(dev)
         world.add_robot(robot)
         tv = [float(v) for v in scene.target_vel[i, r]]

@@ -175,3 +175,23 @@ def test_golden_fixtures(name):
         for key in ("pose", "range", "light", "smell", "stalled"):
             np.testing.assert_allclose(np.array(obs[key], dtype=np.float64), np.array(entry[key], dtype=np.float64),
                                        rtol=1e-12, atol=1e-12, err_msg=key)
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors (kat_vectors: philox4x32 10 rounds) pin the generator the
+    seeded sensor noise is built on -- the CUDA side is then checked against this one."""
+    from oracle import aitk_oracle as orc
+
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kat:
+        assert orc.philox4x32_10(ctr, key) == want, (ctr, key)
+    # the normal variates built on it: mean 0, deviation 1
+    zs = [orc.noise_normal(7, w, orc.NOISE_RANGE, 3, 5) for w in range(4000)]
+    m = sum(zs) / len(zs)
+    sd = (sum((z - m) ** 2 for z in zs) / len(zs)) ** 0.5
+    assert abs(m) < 0.06 and abs(sd - 1.0) < 0.05, (m, sd)

@@ -399,6 +399,86 @@ def test_scan_path_fans_and_config1():
         assert stats["max_rel_dist"] < 1e-5
 
 
+def test_seeded_sensor_noise():
+    """Philox sensor noise: every noisy reading equals the oracle's noise model sample for
+    sample; the residuals have the requested deviation; a reading's noise depends only on (seed,
+    global world index, sensor, step) -- not on the launch plan or on how the batch is sharded."""
+    from oracle import aitk_oracle as orc
+    from oracle import scene_adapter as sa
+
+    seed, rstd, lrel = 0x1234_5678_9ABC, 1.5, 0.05
+    scene = rb.scenes.config3(n_worlds=24)
+
+    def run(sc, env=None, first_world=0, steps=3, noise=True):
+        def go():
+            eng = rb.BatchEngine(sc)
+            if noise:
+                eng.set_noise(seed, range_std=rstd, light_rel_std=lrel, first_world=first_world)
+            for _ in range(steps):
+                eng.step()
+            eng.synchronize()
+            out = {k: eng.download(k) for k in ("range", "light", "pose", "stalled")}
+            eng.close()
+            return out
+
+        return _with_env(env or {}, go)
+
+    noisy, clean = run(scene), run(scene, noise=False)
+    assert np.array_equal(noisy["pose"], clean["pose"])  # noise touches observations only
+    assert not np.array_equal(noisy["range"], clean["range"])
+    # sample-for-sample against the oracle's restatement of the noise model
+    orc.SW.SENSOR_NOISE = {"seed": seed, "range_std": rstd, "light_rel_std": lrel}
+    try:
+        for i in (0, 7, 23):
+            ref = sa.step_and_observe(scene, i, 3, camera=False)
+            np.testing.assert_allclose(noisy["range"][i], ref["range"], rtol=1e-4, atol=2e-4)
+            np.testing.assert_allclose(noisy["light"][i], ref["light"], rtol=1e-4, atol=1e-6)
+    finally:
+        orc.SW.SENSOR_NOISE = None
+    # reproducible, and independent of tiling / launch plan
+    again = run(scene, {"BRS_TW": "3", "BRS_NH": "2"})
+    assert np.array_equal(again["range"], noisy["range"]) and np.array_equal(again["light"], noisy["light"])
+    # a shard that passes its world offset sees the noise of the same global worlds
+    part = run(scene.slice(10, 9), first_world=10)
+    assert np.array_equal(part["range"], noisy["range"][10:19]) and np.array_equal(part["light"], noisy["light"][10:19])
+    # statistics on the solo range path: 64 rays x 512 worlds, residual deviation = range_std
+    sc5 = rb.scenes.config5(n_worlds=512, n_segments=100, n_rays=64)
+    n5 = run(sc5, {"BRS_SOLO": "1"}, steps=1)
+    c5 = run(sc5, {"BRS_SOLO": "1"}, steps=1, noise=False)
+    f5 = run(sc5, {"BRS_SOLO": "0", "BRS_GROUP_MIN": "1"}, steps=1)
+    assert np.array_equal(n5["range"], f5["range"])  # fused kernel, same samples
+    res = (n5["range"] - c5["range"])[(n5["range"] > 0) & (n5["range"] < 200.0) & (c5["range"] < 199.0)]
+    assert res.size > 10000 and abs(res.mean()) < 0.05 and abs(res.std() - rstd) < 0.05, (res.size, res.mean(), res.std())
+
+
+def test_world_json_round_trip_on_the_gpu():
+    """World.to_json -> World.from_json rebuilds a world whose steps equal the original's."""
+    w = rb.World(220, 180)
+    w.add_wall("blue", 50, 40, 120, 45)
+    w.add_wall("red", 160, 30, 170, 150)
+    w.add_bulb("white", 100, 120, 0, 1.0)
+    r = rb.Robot(60, 90, 30)
+    r.add_device(rb.RangeSensor(position=(8, 0), a=0, max=80, width=20))
+    r.add_device(rb.Camera(width=32, height=16))
+    r.add_device(rb.LightSensor(position=(5, 0)))
+    w.add_robot(r)
+    r2 = rb.Robot(150, 60, 200)
+    r2.add_device(rb.RangeSensor(position=(8, 0), a=0, max=60, width=0))
+    w.add_robot(r2)
+    r.move(0.7, 0.2)
+    r2.move(0.4, -0.3)
+    w2 = rb.World.from_json(w.to_json())
+    list(w2)[0].move(0.7, 0.2)
+    list(w2)[1].move(0.4, -0.3)
+    for _ in range(12):
+        w.step()
+        w2.step()
+    for a, b in zip(w, w2):
+        assert (a.x, a.y, a.a, a.stalled) == (b.x, b.y, b.a, b.stalled)
+        assert a[0].get_distance() == b[0].get_distance()
+    assert np.array_equal(np.asarray(list(w)[0][1].take_picture()), np.asarray(list(w2)[0][1].take_picture()))
+
+
 def test_wide_fov_camera_has_no_cone():
     """A 200-degree camera cannot use the cone cull; results still match the oracle."""
     scene = rb.scenes.config2(n_worlds=8, cam_w=64, cam_h=32)
