@@ -8,6 +8,7 @@
 #include "brs_kernels.cuh"
 #include "brs_wide.cuh"
 #include "brs_solo.cuh"
+#include "brs_multi.cuh"
 
 #include <sched.h>
 
@@ -88,6 +89,12 @@ struct brs_engine {
   GroupDev h_scan_group;
   SoloRay* d_scan_rays = nullptr;
   int scan_nrays = 0, scan_SL = 1, scan_NRL = 1;
+  // the solo multi path (brs_multi_kernel): several robots (or several mounts), no camera
+  bool use_rlist = false;  // fused / wide: per-robot lists of reachable segments for the direct-path range sensors
+  bool multi = false;
+  MultiRay* d_multi_rays = nullptr;
+  int multi_nrays = 0, multi_bw = 1;
+  float multi_reach[8] = {};
   // brs_step_host: chunked pipeline (kernel of chunk c+1 overlaps the device->host copies of chunk c)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {}, ev_copied = nullptr;
@@ -404,6 +411,28 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       e->scan_nrays = (int)scan_rays.size();
     }
   }
+  // the solo multi path's view: every range ray of the world, robot by robot, and how far from
+  // its robot's centre a ray can reach (mount offset + range, widened)
+  std::vector<MultiRay> multi_rays;
+  const bool multi_shape = cfg->n_camera == 0 && cfg->seg_cap + 4 * R <= 256 && cfg->n_light * cfg->n_bulbs <= 1024 &&
+                           (cfg->n_range + cfg->n_light + cfg->n_smell) > 0;
+  {
+    for (int r = 0; r < R; ++r) {
+      double reach = 0;
+      for (int i = 0; i < cfg->n_range; ++i) {
+        if (gdev[i].robot != r) continue;
+        for (int q = 0; q < gdev[i].n_rays && multi_shape; ++q) {
+          MultiRay mr;
+          mr.cr = gdev[i].cr[q]; mr.sr = gdev[i].sr[q]; mr.max = gdev[i].max; mr.mx = gdev[i].mx; mr.my = gdev[i].my;
+          mr.sensor = i; mr.robot = r;
+          multi_rays.push_back(mr);
+        }
+        reach = std::fmax(reach, std::hypot(gdev[i].mx, gdev[i].my) + gdev[i].max);
+      }
+      e->multi_reach[r] = (float)(reach * (1.0 + 1e-3) + 0.1);
+    }
+    e->multi_nrays = (int)multi_rays.size();
+  }
   std::vector<int> gr_idx, dr_idx;
   for (int i = 0; i < cfg->n_range; ++i) (gdev[i].group >= 0 ? gr_idx : dr_idx).push_back(i);
   e->n_group = (int)groups.size();
@@ -433,7 +462,8 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       (rc = to_device(&e->d_groups, groups)) || (rc = to_device(&e->d_gr_idx, gr_idx)) ||
       (rc = to_device(&e->d_dr_idx, dr_idx)) ||
       (rc = to_device(&e->d_rowsky, rowsky)) || (rc = to_device(&e->d_rowgnd, rowgnd)) ||
-      (scan_shape && (rc = to_device(&e->d_scan_rays, scan_rays)))) {
+      (scan_shape && (rc = to_device(&e->d_scan_rays, scan_rays))) ||
+      (multi_shape && (rc = to_device(&e->d_multi_rays, multi_rays)))) {
     brs_destroy(e);
     return rc;
   }
@@ -486,8 +516,14 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->gtasks = gtasks;
   e->dtasks = dtasks;
   const int tasks = std::max(gtasks + dtasks, 1);
+  // (direct-path range sensors search per-robot lists of the segments within reach: two byte
+  //  arrays behind the kernel's own shared-memory layout)
+  e->use_rlist = e->n_dr > 0 && cfg->seg_cap + 4 * R <= 256 && env_int("BRS_RLIST", 0) != 0;  // (measured on config 3: building the lists costs what the shorter searches save; opt-in)
+  auto rl_extra = [&](int tw) {
+    return e->use_rlist ? align_up(tw * R * (cfg->seg_cap + 4 * R), 16) + align_up(tw * R * 4, 16) : 0;
+  };
   auto smem_shape = [&](int tw, bool big) {
-    return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h, !big).total;
+    return make_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h, !big).total + rl_extra(tw);
   };
   // small shape (128 workers, 4 CTAs/SM, TMA-staged walls) unless one world's footprint leaves
   // room for <= 2 such CTAs; the big shape (256 workers) reads walls from L2 instead of staging
@@ -586,7 +622,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   {
     // (one-warp teams read the camera tables through L1: see make_wide_layout)
     auto wsmem_nt = [&](int tw, bool big, int nt_) {
-      return make_wide_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h, !big, nt_ > 32).total;
+      return make_wide_layout(tw, cfg->seg_cap, R, e->n_group, cfg->n_camera, e->cam_w, e->cam_h, !big, nt_ > 32).total + rl_extra(tw);
     };
     auto wsmem = [&](int tw, bool big) { return wsmem_nt(tw, big, 32); };
     const int target_warps = env_int("BRS_WWARPS", 20);
@@ -765,6 +801,39 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       if (e->scan) { e->solo = true; e->wide = false; e->prep_fused = false; }  // (solo = "a warp-per-world plan is active")
     }
   }
+  // ---- the solo multi path: launch geometry -------------------------------------
+  if (multi_shape && !e->solo) {
+    const int bw = std::max(1, 16 / pow2ceil(R));
+    e->multi_bw = bw;
+    const MultiLayout ML = make_multi_layout(R, bw, cfg->seg_cap + 4 * R, cfg->n_range, cfg->n_light, cfg->n_bulbs);
+    const int variant = env_int("BRS_SOLO_CTAS", 6);
+    const void* mk = variant >= 8 ? (const void*)brs_multi_kernel<128, 8>
+                     : variant <= 4 ? (const void*)brs_multi_kernel<128, 4>
+                     : variant == 5 ? (const void*)brs_multi_kernel<128, 5> : (const void*)brs_multi_kernel<128, 6>;
+    e->sNT = 128;
+    e->s_smem = ML.per_warp * 4;
+    e->s_kfn = mk;
+    bool ok = (size_t)e->s_smem <= prop.sharedMemPerBlockOptin;
+    int snb = 0;
+    if (ok) {
+      ce = cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, e->s_smem);
+      if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&snb, mk, e->sNT, e->s_smem);
+      ok = ce == cudaSuccess && snb >= 1;
+      if (!ok) cudaGetLastError();
+    }
+    if (ok) {
+      snb = std::min(snb, env_int("BRS_SOLO_MAX_CTAS", 32));
+      e->s_warps_per_sm = snb * 4;
+      e->s_ctas_per_sm = snb;
+      e->s_grid = std::max(1, std::min((cfg->n_worlds + 3) / 4, snb * e->sm_count));
+      // measured (profiles/r2, config 3): 0.22 ms against the fused kernel's 0.20 -- a warp alone
+      // leaves most lanes idle in the per-robot phases that a 15-world tile fills -- so this plan
+      // is opt-in (BRS_MULTI=1), kept bit-exact by the tests
+      e->multi = env_int("BRS_MULTI", 0) != 0;
+      e->solo_interleave = env_int("BRS_SOLO_INTERLEAVE", 1) != 0;
+      if (e->multi) { e->solo = true; e->wide = false; e->prep_fused = false; }
+    }
+  }
   // ---- brs_step_host pipeline: a copy stream and the events that chain it to the caller's
   e->host_chunks = std::max(1, std::min(8, env_int("BRS_HOST_CHUNKS", cfg->n_worlds >= 8192 ? 4 : 1)));
   ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
@@ -815,6 +884,7 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_ws);
   cudaFree(e->d_counters);
   cudaFree(e->d_scan_rays);
+  cudaFree(e->d_multi_rays);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (int k = 0; k < 8; ++k)
     if (e->ev_chunk[k]) cudaEventDestroy(e->ev_chunk[k]);
@@ -952,6 +1022,18 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
   p.s_robot = e->h_robot0; p.s_camera = e->h_camera0; p.s_group = e->h_group0;
   p.s_sky = e->h_sky0; p.s_gnd = e->h_gnd0;
   p.solo_interleave = e->solo_interleave;
+  for (int r = 0; r < 8; ++r) p.m_reach[r] = e->multi_reach[r];
+  if (e->multi) {
+    p.m_rays = e->d_multi_rays; p.m_nrays = e->multi_nrays; p.m_bw = e->multi_bw;
+  }
+  if (e->use_rlist && !e->solo) {
+    const int tw = wide ? e->wTW : e->TW, R = c.n_robots, nvis = c.seg_cap + 4 * R;
+    const int base = wide ? make_wide_layout(tw, c.seg_cap, R, e->n_group, c.n_camera, e->cam_w, e->cam_h, !e->w_big, e->wNT > 32).total
+                          : make_layout(tw, c.seg_cap, R, e->n_group, c.n_camera, e->cam_w, e->cam_h, !e->big).total;
+    p.use_rlist = 1;
+    p.rl_off = base;
+    p.rc_off = base + align_up(tw * R * nvis, 16);
+  }
   if (e->scan) {
     p.s_group = e->h_scan_group;
     p.s_rays = e->d_scan_rays; p.s_nrays = e->scan_nrays; p.s_SL = e->scan_SL;
@@ -1185,7 +1267,7 @@ extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem
 
 extern "C" int brs_path_info(brs_engine* e, int* wide, int* launches_per_step) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_path_info: null engine");
-  if (wide) *wide = e->scan ? 4 : e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
+  if (wide) *wide = e->multi ? 5 : e->scan ? 4 : e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
   if (launches_per_step) *launches_per_step = (!e->solo && (e->wide || e->prep_fused)) ? 2 : 1;
   return BRS_OK;
 }

@@ -118,6 +118,7 @@ __host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
 }
 
 struct SoloRay;
+struct MultiRay;
 // Seeded sensor noise (off unless brs_set_noise enabled it): one Philox4x32-10 block per
 // (world, sensor, step) -- counter = (global world index, kind << 24 | sensor, step lo, step hi),
 // key = the 64-bit seed -- so a reading's noise depends on nothing but those four numbers:
@@ -190,6 +191,13 @@ struct KParams {
   // the solo range path (brs_scan_kernel): every ray of the robot's one mount
   const struct SoloRay* s_rays;  // [s_nrays]
   int s_nrays, s_SL;             // rays per world; lanes that share one ray (power of two)
+  // the solo multi path (brs_multi_kernel): several robots, no camera
+  const struct MultiRay* m_rays;  // [m_nrays] every range ray of the world, robot by robot
+  int m_nrays, m_bw;              // rays per world; worlds per PREP batch
+  float m_reach[8];               // per robot: how far from its centre its range rays can reach
+  // fused / wide paths, direct-path range sensors: per (world, robot) lists of the segments within
+  // m_reach of the robot (shared memory behind the kernel's own layout; 0 = search every segment)
+  int use_rlist, rl_off, rc_off;
 };
 
 // per-column paint record
@@ -519,20 +527,26 @@ __device__ __forceinline__ void group_max(uint32_t& key, int& idx, int SL, uint3
 // the ray parameter t (unsigned order == float order for t >= 0; negative / NaN
 // / inf parameters compare above BRS_KEY_NOHIT), smaller is nearer.
 #define BRS_KEY_NOHIT 0x3F800001u  // just above 1.0f: parameters <= 1 are hits
+// the two ray parameters of one (ray, segment) pair as bit patterns: tb = t along the ray,
+// ub = u along the segment (one definition, so that every path rounds alike)
+__device__ __forceinline__ void direct_test(const float4 s, float ox, float oy, float rx, float ry, uint32_t& tb,
+                                            uint32_t& ub) {
+  const float dx = ox - s.x, dy = oy - s.y;
+  const float den = s.w * rx - s.z * ry;
+  const float na = s.z * dy - s.w * dx;
+  const float nb = rx * dy - ry * dx;
+  const float inv = rcp_approx(den);
+  tb = __float_as_uint(na * inv);
+  ub = __float_as_uint(nb * inv);
+}
 template <bool SL1>
 __device__ BRS_INL_DIRECT void search_direct(const float4* __restrict__ segtab, int j0, int j1, int g, int SLrt,
                                               float ox, float oy, float rx, float ry, uint32_t& key, int& idx) {
   const int SL = SL1 ? 1 : SLrt;
 #pragma unroll 4
   for (int j = j0 + (SL1 ? 0 : g); j < j1; j += SL) {
-    const float4 s = segtab[j];
-    const float dx = ox - s.x, dy = oy - s.y;
-    const float den = s.w * rx - s.z * ry;
-    const float na = s.z * dy - s.w * dx;
-    const float nb = rx * dy - ry * dx;
-    const float inv = rcp_approx(den);
-    const uint32_t tb = __float_as_uint(na * inv);
-    const uint32_t ub = __float_as_uint(nb * inv);
+    uint32_t tb, ub;
+    direct_test(segtab[j], ox, oy, rx, ry, tb, ub);
     if (ub <= 0x3F800000u && tb <= key) {
       key = tb;
       idx = j;
@@ -962,10 +976,50 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
 // device kind: mixing kinds in a warp would serialise their code paths.  Either team can
 // run this: the workers for sensor-heavy worlds, the otherwise idle helper team for
 // camera worlds with a few extra sensors (right after it committed the tile's poses).
-__device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, int lane, int w0, int nw,
+__device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, int bid, int lane, int w0, int nw,
                                              const uint32_t* __restrict__ rawb, const float4* __restrict__ segtab,
                                              const double* __restrict__ wsb, const int2* __restrict__ meta) {
   const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
+  extern __shared__ __align__(128) unsigned char brs_dyn_smem[];
+  uint8_t* const rlist = (uint8_t*)(brs_dyn_smem + p.rl_off);
+  int* const rcnt = (int*)(brs_dyn_smem + p.rc_off);
+  const bool use_rlist = p.use_rlist && p.n_dr > 0;
+  if (use_rlist) {
+    // Which segments can a robot's range rays reach at all?  One warp per (world, robot): FP32
+    // distance of the final centre to every segment (walls and the other robots' box edges)
+    // against the reach of the robot's sensors (mount offset + range, widened on the host),
+    // survivors compacted in index order.  The searches below then run over these lists: in a
+    // 300 x 300 room with 60-unit sensors two segments in three drop out, exactly.
+    const int tw = tt >> 5, nwarp = tn >> 5;
+    for (int pg = tw; pg < nw * R; pg += nwarp) {
+      const int wl = (int)fdiv(pg, p.dR), r = pg - wl * R;
+      const int S = meta[wl].x, nseg = S + 4 * R, own = S + 4 * r;
+      const double* wsr = wsb + (size_t)pg * BRS_WS_STRIDE;
+      const float cx = (float)wsr[BRS_WS_POSE], cy = (float)wsr[BRS_WS_POSE + 1];
+      const float reach = p.m_reach[r], reach2 = reach * reach;
+      const float4* st = segtab + (size_t)wl * nvis;
+      uint8_t* li = rlist + (size_t)pg * nvis;
+      int n = 0;
+      for (int j0 = 0; j0 < nseg; j0 += 32) {
+        const int j = j0 + lane;
+        bool keep = false;
+        if (j < nseg && (unsigned)(j - own) >= 4u) {
+          const float4 sg = st[j];
+          const float dx = cx - sg.x, dy = cy - sg.y;
+          const float ee = fmaf(sg.z, sg.z, sg.w * sg.w);
+          float h = fmaf(dx, sg.z, dy * sg.w) * rcp_approx(ee);
+          h = fminf(fmaxf(h, 0.f), 1.f);
+          const float vx = fmaf(-h, sg.z, dx), vy = fmaf(-h, sg.w, dy);
+          keep = !(fmaf(vx, vx, vy * vy) > reach2);  // (NaN keeps the segment)
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) li[n + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)j;
+        n += __popc(bal);
+      }
+      if (lane == 0) rcnt[pg] = n;
+    }
+    team_sync(bid, tn);
+  }
   // range sensors on their own mount ...
   if (p.n_dr > 0) {
     const int SL = p.SLD, g = tt & (SL - 1), slot = tt / SL, nslot = tn / SL;
@@ -993,7 +1047,21 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
         const float rx = (float)ds(x2, x1), ry = (float)ds(y2, y1);
         uint32_t key = BRS_KEY_NOHIT;
         int idx = -1;
-        if (SL == 1) {
+        if (use_rlist) {
+          const uint8_t* li = rlist + (size_t)(wl * R + r) * nvis;
+          const int n = rcnt[wl * R + r];
+#pragma unroll 4
+          for (int q = g; q < n; q += SL) {
+            const int j = li[q];
+            uint32_t tb, ub;
+            direct_test(st[j], ox, oy, rx, ry, tb, ub);
+            if (ub <= 0x3F800000u && tb <= key) {
+              key = tb;
+              idx = j;
+            }
+          }
+          if (SL > 1) group_min(key, idx, SL, gmask);
+        } else if (SL == 1) {
           search_direct<true>(st, 0, own_lo, 0, 1, ox, oy, rx, ry, key, idx);
           search_direct<true>(st, own_hi, nseg, 0, 1, ox, oy, rx, ry, key, idx);
         } else {
@@ -1348,7 +1416,7 @@ __device__ BRS_INL_ROBOT void collide_commit_tile(const KParams& p, int w0, int 
   // do not -- run the direct-path sensors of this tile here, on the poses just committed
   if (do_direct) {
     team_sync(bid, nth);
-    sense_direct(p, ht, nth, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta);
+    sense_direct(p, ht, nth, bid, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta);
   }
   BRS_PH(ht == 0, 13);
 }
@@ -1582,7 +1650,7 @@ __device__ __forceinline__ void sense_paint_tile(const KParams& p, const int tid
         }
       }
       // 5b. direct path (unless the helper team already ran it for this tile)
-      if (do_sense && direct_here) sense_direct(p, tid, NW, lane, w0, nw, rawb, segtab, wsb, meta);
+      if (do_sense && direct_here) sense_direct(p, tid, NW, 1, lane, w0, nw, rawb, segtab, wsb, meta);
 
       BRS_PH(tid == 0, 2);
       // ---------------- PAINT ----------------------------------------------------------------

@@ -70,9 +70,10 @@ __host__ __device__ inline SoloLayout make_solo_layout(int seg_cap) {
 // One half of Robot.step's proposal for the solo record: the same operations, in the same
 // order, as prep_robot_half (brs_kernels.cuh) minus the box corners (a lone robot's box is
 // only needed when a wall falls inside its disc; collide() rebuilds it there).
-__device__ __forceinline__ void solo_prep_half(const KParams& p, const RobotDev& rd, int w, bool prop,
-                                               double* __restrict__ r) {
-  const size_t o = (size_t)w * 3;
+// (R robots per world, this is robot `ri`: the multi path shares the function)
+__device__ __forceinline__ void solo_prep_half_at(const KParams& p, const RobotDev& rd, int w, int R, int ri, bool prop,
+                                                  double* __restrict__ r) {
+  const size_t o = ((size_t)w * R + ri) * 3;
   const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
   const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
   double vx = v0, vy = v1, va = v2, pa = a;
@@ -102,6 +103,10 @@ __device__ __forceinline__ void solo_prep_half(const KParams& p, const RobotDev&
     const float ext = fmaxf(p.world_size[2 * w], p.world_size[2 * w + 1]);
     *(int2*)(r + BRS_SR_META) = make_int2(S, __float_as_int(ext));
   }
+}
+__device__ __forceinline__ void solo_prep_half(const KParams& p, const RobotDev& rd, int w, bool prop,
+                                               double* __restrict__ r) {
+  solo_prep_half_at(p, rd, w, 1, 0, prop, r);
 }
 
 // The warp's staged wall store seen from one lane: the four SoA rows at this lane's column, so

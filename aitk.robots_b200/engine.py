@@ -259,7 +259,8 @@ class BatchEngine:
         cabi.check(self._lib.brs_path_info(self._h, C.byref(wide), C.byref(nl)))
         return {"path": ("fused (one kernel)", "wide (prep + step kernel, PDL)", "fused fed by the prep kernel (PDL)",
                          "solo (one warp per world, one kernel)",
-                         "solo range (one warp per world, walls streamed, one kernel)")[wide.value],
+                         "solo range (one warp per world, walls streamed, one kernel)",
+                         "solo multi (one warp per world, several robots, one kernel)")[wide.value],
                 "launches_per_step": nl.value, "threads": t.value, "ctas": c.value, "smem_bytes": s.value,
                 "sm_count": m.value, "worlds_per_tile": tw.value, "tiles": nt.value, "workers": nw.value,
                 "cols_per_thread": nr.value, "ray_groups": ng.value}

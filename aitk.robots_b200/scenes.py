@@ -331,6 +331,37 @@ def config2(n_worlds=4096, seed=2000, first_world=0, cam_w=256, cam_h=128):
     return _assemble("config2", w, h, segs, colors, [robot], rng, B)
 
 
+def config2_boxes(n_worlds=4096, seed=2100, first_world=0, cam_w=256, cam_h=128, n_boxes=20):
+    """The other reading of BASELINE.json configs[1] ("a 20-wall room" = 20 box-shaped walls, as
+    upstream ``World.add_wall(..., box=True)`` makes them): 80 wall segments + the boundary."""
+    rng = _rng(seed, first_world)
+    w, h, B = 300.0, 200.0, n_worlds
+    bx = np.array(_boundary(w, h), dtype=np.float32)
+    cx = rng.uniform(15, w - 15, (B, n_boxes))
+    cy = rng.uniform(15, h - 15, (B, n_boxes))
+    hw = rng.uniform(2.0, 12.0, (B, n_boxes))
+    hh = rng.uniform(2.0, 12.0, (B, n_boxes))
+    x0, x1_, y0, y1_ = cx - hw, cx + hw, cy - hh, cy + hh
+    # four edges per box, in add_wall(box=True) order
+    ex1 = np.stack([x0, x1_, x1_, x0], axis=2).reshape(B, -1)
+    ey1 = np.stack([y0, y0, y1_, y1_], axis=2).reshape(B, -1)
+    ex2 = np.stack([x1_, x1_, x0, x0], axis=2).reshape(B, -1)
+    ey2 = np.stack([y0, y1_, y1_, y0], axis=2).reshape(B, -1)
+    r = [a.astype(np.float32) for a in (ex1, ey1, ex2, ey2)]
+    segs = [np.concatenate([np.tile(bx[None, :, k], (B, 1)), r[k]], axis=1) for k in range(4)]
+    box_col = PALETTE[rng.integers(0, 8, (B, n_boxes))]
+    colors = np.concatenate(
+        [np.tile(np.array([[(128, 0, 128, 255)] * 4], dtype=np.uint8), (B, 1, 1)), np.repeat(box_col, 4, axis=1)], axis=1)
+    robot = RobotSpec(
+        devices=[
+            RangeSpec(position=(7.0, -3.0), a=30.0, max=100.0, width=0.0, name="left-ir"),
+            RangeSpec(position=(7.0, 3.0), a=-30.0, max=100.0, width=0.0, name="right-ir"),
+            CameraSpec(width=cam_w, height=cam_h, a=60.0),
+        ]
+    )
+    return _assemble("config2-boxes", w, h, segs, colors, [robot], rng, B, tries=2000)
+
+
 def config3(n_worlds=65536, seed=3000, first_world=0):
     """4 robots each with a 16-ray range fan + LightSensor, 2 bulbs, 12 wall segments."""
     rng = _rng(seed, first_world)

@@ -33,6 +33,8 @@ def make_scene(rb, config, n_worlds, first_world):
         return g.config1(n_worlds=n_worlds, first_world=first_world)
     if config == "config2":
         return g.config2(n_worlds=n_worlds, first_world=first_world)
+    if config == "config2-boxes":
+        return g.config2_boxes(n_worlds=n_worlds, first_world=first_world)
     if config == "config3":
         return g.config3(n_worlds=n_worlds, first_world=first_world)
     if config == "config4":
@@ -43,7 +45,7 @@ def make_scene(rb, config, n_worlds, first_world):
     raise SystemExit("unknown config %r" % config)
 
 
-DEFAULT_WORLDS = {"config1": 4096, "config2": 4096, "config3": 65536, "config4": 131072}
+DEFAULT_WORLDS = {"config1": 4096, "config2": 4096, "config2-boxes": 4096, "config3": 65536, "config4": 131072}
 
 
 def describe(config, scene):
@@ -693,6 +695,8 @@ def main():
             e1.close()
             w, _, _ = bench.workload("config1", 4096, steps_x, 3)
             ex["config1_x4096"] = summarize(w)
+            w, _, _ = bench.workload("config2-boxes", 4096, steps_x, 3)
+            ex["config2_boxes"] = summarize(w)  # the "20 boxes = 80 segments" reading of configs[1]
             w, _, _ = bench.workload("config3", DEFAULT_WORLDS["config3"], steps_x, 3)
             ex["config3"] = summarize(w)
         # config 4: 1,048,576 worlds split over the ranks (N = 1: one eighth, the 8-GPU shard)

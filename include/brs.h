@@ -227,7 +227,8 @@ int brs_tile_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* worker
  * programmatic dependent launch; see csrc/brs_wide.cuh), 2: the fused kernel fed by the prep
  * kernel (its helper team skips the float64 pose proposal), 3: the solo path (one warp per
  * one-robot camera world, one launch; see csrc/brs_solo.cuh), 4: the solo range path (one warp
- * per world for a lone robot whose range sensors share one mount, no camera).  All produce
+ * per world for a lone robot whose range sensors share one mount, no camera), 5: the solo multi
+ * path (one warp per world for several robots without cameras).  All produce
  * identical bits (paths 0-3; path 4 searches every ray through the shared-origin table, which
  * the other paths do for mounts with >= BRS_GROUP_MIN rays).
  * *launches_per_step = kernels one brs_step enqueues. */

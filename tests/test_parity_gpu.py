@@ -60,6 +60,14 @@ def test_config2_camera_and_range():
     assert stats["pixel_mismatch"] <= 0.001 * stats["pixels"]
 
 
+def test_config2_boxes_reading():
+    """The "20 boxes = 80 segments" reading of BASELINE.json configs[1]."""
+    scene = rb.scenes.config2_boxes(n_worlds=32, cam_w=64, cam_h=32)
+    stats = parity.compare(scene, n_steps=3, worlds=range(0, 32, 4))
+    assert stats["max_rel_dist"] < 1e-5
+    assert stats["pixel_mismatch"] <= 0.002 * stats["pixels"]
+
+
 def test_config3_multi_robot_collisions_and_light():
     scene = rb.scenes.config3(n_worlds=64)
     stats = parity.compare(scene, n_steps=20, worlds=range(0, 64, 4), camera=False)
@@ -229,6 +237,7 @@ def test_culling_and_tiling_never_change_results(maker):
                 {"BRS_WIDE": "0", "BRS_NO_CONE": "1", "BRS_NO_RANGE_CULL": "1"}, {"BRS_WIDE": "0", "BRS_TW": "1"},
                 {"BRS_WIDE": "0", "BRS_TW": "5", "BRS_BIG": "1"},
                 {"BRS_WIDE": "0", "BRS_NH": "2"}, {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "1"},
+                {"BRS_WIDE": "0", "BRS_RLIST": "1"}, {"BRS_WIDE": "1", "BRS_RLIST": "1", "BRS_WNT": "64"},
                 {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
                 {"BRS_WIDE": "0", "BRS_NR": "1", "BRS_GROUP_MIN": "1000"},
                 {"BRS_WIDE": "0", "BRS_PREP": "1"}, {"BRS_WIDE": "0", "BRS_PREP": "1", "BRS_TW": "3", "BRS_BIG": "1"},
@@ -479,6 +488,57 @@ def test_world_json_round_trip_on_the_gpu():
     assert np.array_equal(np.asarray(list(w)[0][1].take_picture()), np.asarray(list(w2)[0][1].take_picture()))
 
 
+@pytest.mark.parametrize("maker", [
+    lambda: rb.scenes.config3(n_worlds=70),
+    lambda: _crowd_scene(13, 2, camera=False, extras=True),
+    lambda: _crowd_scene(13, 5, camera=False, extras=True),
+    lambda: _crowd_scene(9, 8, camera=False, extras=True),
+    lambda: _crowd_scene(11, 3, camera=False),
+])
+def test_multi_path_bit_identical_and_matches_the_oracle(maker):
+    """The solo multi path (one warp per world, several robots; brs_multi_kernel) against the
+    fused kernel, bit for bit, over 40 steps of crowded rooms (robot-robot and robot-wall
+    collisions, list-order replay, fans, lights behind robots, smell), and against the oracle."""
+    scene = maker()
+    steps = 40
+
+    def multi():
+        eng = rb.BatchEngine(scene)
+        assert eng.launch_info()["path"].startswith("solo multi"), eng.launch_info()
+        eng.close()
+        return parity.run_engine(scene, steps)
+
+    a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0"}, lambda: parity.run_engine(scene, steps))
+    for env in ({"BRS_MULTI": "1"}, {"BRS_MULTI": "1", "BRS_SOLO_INTERLEAVE": "0", "BRS_SOLO_CTAS": "8"}):
+        b = _with_env(env, multi)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, env)
+    assert a["stalled"].any() or scene.n_robots < 3
+    stats = parity.compare_outputs(scene, b, steps, range(0, scene.n_worlds, 3), camera=False)
+    assert stats["max_pose_err"] < 1e-9 and stats["max_rel_dist"] < 1e-5
+
+
+def test_multi_path_step_flags():
+    """Move-only and sense-only steps of the solo multi path equal the fused kernel's."""
+    scene = _crowd_scene(20, 4, camera=False, extras=True)
+
+    def run():
+        eng = rb.BatchEngine(scene)
+        outs = []
+        for flags in (rb.STEP_SENSE, rb.STEP_MOVE, rb.STEP_MOVE, rb.STEP_SENSE, rb.STEP_ALL, rb.STEP_ALL):
+            eng.step(flags=flags)
+            eng.synchronize()
+            outs.append({k: eng.download(k) for k in ("pose", "vel", "stalled", "range", "light", "smell")})
+        eng.close()
+        return outs
+
+    a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0"}, run)
+    b = _with_env({"BRS_MULTI": "1"}, run)
+    for x, y in zip(a, b):
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+
+
 def test_wide_fov_camera_has_no_cone():
     """A 200-degree camera cannot use the cone cull; results still match the oracle."""
     scene = rb.scenes.config2(n_worlds=8, cam_w=64, cam_h=32)
@@ -523,7 +583,7 @@ def test_many_steps_stalled_robots_config4():
     assert stats["max_pose_err"] < 1e-9
 
 
-def _crowd_scene(n_worlds, n_robots, seed=11):
+def _crowd_scene(n_worlds, n_robots, seed=11, camera=True, extras=False):
     """Many robots in a small room: robot-robot collisions are frequent (exercises the
     list-order replay on the pair masks up to BRS_MAX_ROBOTS)."""
     import math
@@ -537,10 +597,23 @@ def _crowd_scene(n_worlds, n_robots, seed=11):
     robots = []
     for k in range(n_robots):
         devs = [g.RangeSpec(position=(8.0, 0.0), a=0.0, max=60.0, width=20.0 if k % 2 else 0.0)]
-        if k == 0:
+        if k == 0 and camera:
             devs.append(g.CameraSpec(width=32, height=16, a=90.0))
+        if extras:
+            devs.append(g.LightSpec(position=(4.0, 1.0 * k)))
+            if k % 3 == 0:
+                devs.append(g.SmellSpec(position=(3.0, 0.0)))
+                devs.append(g.RangeSpec(position=(-5.0, 2.0), a=170.0, max=45.0, width=0.0))
         robots.append(g.RobotSpec(rgba=tuple(int(c) for c in g.PALETTE[k % 8]), height=0.3 + 0.05 * k, devices=devs))
-    scene = g._assemble("crowd", w, h, segs, colors, robots, rng, B)
+    bulbs = food = None
+    if extras:
+        bulbs = np.zeros((B, 3, 4), dtype=np.float32)
+        bulbs[:, :, 0] = rng.uniform(10, w - 10, (B, 3))
+        bulbs[:, :, 1] = rng.uniform(10, h - 10, (B, 3))
+        bulbs[:, :, 3] = rng.uniform(0.5, 2.0, (B, 3))
+        food = np.stack([rng.uniform(10, w - 10, (B, 1)), rng.uniform(10, h - 10, (B, 1)), np.full((B, 1), 20.0)], axis=2)
+    scene = g._assemble("crowd", w, h, segs, colors, robots, rng, B, bulbs=bulbs, food=food,
+                        smell_cell=10.0 if extras else 0.0)
     scene.target_vel[:, :, 0] = rng.uniform(1.0, 2.0, (B, n_robots))
     return scene
 

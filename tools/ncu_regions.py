@@ -16,7 +16,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = {n: os.path.join(ROOT, "aitk.robots_b200", "csrc", n) for n in ("brs_kernels.cuh", "brs_wide.cuh", "brs_solo.cuh")}
+SRC = {n: os.path.join(ROOT, "aitk.robots_b200", "csrc", n) for n in ("brs_kernels.cuh", "brs_wide.cuh", "brs_solo.cuh", "brs_multi.cuh")}
 
 
 def region_marks(path):
