@@ -127,6 +127,11 @@ SYMBOLS = [
     ("brs_upload", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     ("brs_download", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P]),
     ("brs_step", C.c_int, [_P, C.c_double, C.c_uint, _P]),
+    ("brs_bind_peer_outputs", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("brs_peer_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    ("brs_peer_free", C.c_int, [_P, _P]),
+    ("brs_peer_open", C.c_int, [_P, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    ("brs_peer_close", C.c_int, [_P, _P]),
     ("brs_set_noise", C.c_int, [_P, C.c_ulonglong, C.c_uint, C.c_double, C.c_double]),
     ("brs_step_counted", C.c_int, [_P, C.c_double, C.c_uint, _P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     ("brs_step_host", C.c_int, [_P, C.c_double, C.c_uint, _P, _P, _P, _P, _P, _P, _P, _P]),

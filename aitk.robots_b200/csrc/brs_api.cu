@@ -99,6 +99,9 @@ struct brs_engine {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {}, ev_copied = nullptr;
   int host_chunks = 4;
+  // fused picture gather: peer copies of the camera output (brs_bind_peer_outputs)
+  int n_peers = 0;
+  void* peer_cam[7] = {};
   // seeded sensor noise (brs_set_noise); the step counter advances once per sensing step
   NoiseParams noise = {};
   unsigned long long noise_step = 0;
@@ -910,6 +913,68 @@ extern "C" int brs_bind_output(brs_engine* e, int which, void* device_ptr) {
   return BRS_OK;
 }
 
+// The fused gather: observation `which` is ALSO stored, by the kernel that produces it, at
+// peer_ptrs[k] for k < n_peers -- peer-GPU memory mapped into this process (CUDA IPC / peer
+// access), laid out like the engine's own output.  With every rank's slice of every rank's
+// gather buffer bound this way, the step leaves the complete training batch on every GPU and
+// only a stream barrier across the ranks remains of the collective.
+extern "C" int brs_bind_peer_outputs(brs_engine* e, int which, int n_peers, void* const* peer_ptrs) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_bind_peer_outputs: null engine");
+  if (n_peers < 0 || n_peers > 7 || (n_peers && !peer_ptrs)) return fail(BRS_ERR_INVALID, "brs_bind_peer_outputs: 0..7 peers");
+  if (n_peers == 0) {
+    e->n_peers = 0;
+    return BRS_OK;
+  }
+  if (which != BRS_BUF_CAMERA || !e->solo || e->scan || e->multi)
+    return fail(BRS_ERR_UNSUPPORTED, "brs_bind_peer_outputs: only the pictures of the solo launch plan are stored to peers");
+  for (int k = 0; k < n_peers; ++k) {
+    if (!peer_ptrs[k] || ((uintptr_t)peer_ptrs[k] & 15)) return fail(BRS_ERR_INVALID, "brs_bind_peer_outputs: pointers must be 16-byte aligned");
+    e->peer_cam[k] = peer_ptrs[k];
+  }
+  e->n_peers = n_peers;
+  return BRS_OK;
+}
+
+// Gather buffers that other processes can map: plain cudaMalloc memory plus its CUDA IPC handle
+// (64 bytes, to be sent to the peers by whatever transport the host code has), and the peer
+// side: map a handle into this process with peer access from this engine's GPU enabled.
+extern "C" int brs_peer_alloc(brs_engine* e, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!e || !dev_ptr || !handle64) return fail(BRS_ERR_INVALID, "brs_peer_alloc: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  CK(cudaSetDevice(e->cfg.device));
+  void* ptr = nullptr;
+  CK(cudaMalloc(&ptr, std::max<size_t>(bytes, 256)));
+  cudaIpcMemHandle_t h;
+  cudaError_t ce = cudaIpcGetMemHandle(&h, ptr);
+  if (ce != cudaSuccess) {
+    cudaFree(ptr);
+    return fail(BRS_ERR_CUDA, std::string("brs_peer_alloc: cudaIpcGetMemHandle: ") + cudaGetErrorString(ce));
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = ptr;
+  return BRS_OK;
+}
+extern "C" int brs_peer_free(brs_engine* e, void* dev_ptr) {
+  if (e) cudaSetDevice(e->cfg.device);
+  if (dev_ptr) CK(cudaFree(dev_ptr));
+  return BRS_OK;
+}
+extern "C" int brs_peer_open(brs_engine* e, const unsigned char* handle64, void** dev_ptr) {
+  if (!e || !dev_ptr || !handle64) return fail(BRS_ERR_INVALID, "brs_peer_open: null argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* ptr = nullptr;
+  CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = ptr;
+  return BRS_OK;
+}
+extern "C" int brs_peer_close(brs_engine* e, void* dev_ptr) {
+  if (e) cudaSetDevice(e->cfg.device);
+  if (dev_ptr) CK(cudaIpcCloseMemHandle(dev_ptr));
+  return BRS_OK;
+}
+
 static int copy_range(brs_engine* e, int which, int first, int n, size_t* off, size_t* bytes) {
   if (!e || which < 0 || which >= BRS_BUF_COUNT_) return fail(BRS_ERR_INVALID, "copy: bad buffer id");
   if (n < 0) n = e->cfg.n_worlds - first;
@@ -955,6 +1020,8 @@ static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned fl
   p.light_out = (float*)cur(e, BRS_BUF_LIGHT);
   p.smell_out = (float*)cur(e, BRS_BUF_SMELL);
   p.counters = e->counting ? e->d_counters : nullptr;
+  p.n_peers = (e->solo && !e->scan && !e->multi) ? e->n_peers : 0;
+  for (int k = 0; k < p.n_peers; ++k) p.peer_delta[k] = (long long)((char*)e->peer_cam[k] - (char*)p.cam_out);
   p.noise = e->noise;
   p.noise.step_lo = (uint32_t)(e->noise_step & 0xffffffffull);
   p.noise.step_hi = (uint32_t)(e->noise_step >> 32);

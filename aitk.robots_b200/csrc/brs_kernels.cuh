@@ -188,6 +188,11 @@ struct KParams {
   uint32_t s_sky, s_gnd;  // flat sky / ground colours (row 0 of the row tables)
   int solo_interleave;    // warp gw takes worlds gw, gw + n_warps, ... (else: consecutive ranges)
   NoiseParams noise;
+  // fused picture gather (brs_bind_peer_outputs): the solo kernel's PAINT also stores every
+  // quad into the gather buffers of n_peers other GPUs (peer memory over NVLink), at these byte
+  // offsets from cam_out
+  int n_peers;
+  long long peer_delta[7];
   // the solo range path (brs_scan_kernel): every ray of the robot's one mount
   const struct SoloRay* s_rays;  // [s_nrays]
   int s_nrays, s_SL;             // rays per world; lanes that share one ray (power of two)

@@ -199,8 +199,19 @@ __device__ __forceinline__ bool solo_collide(const KParams& p, const RobotDev& r
 // Q = 8*NR quads, 32 / Q rows per warp store, every store covers 512 contiguous bytes.
 // rec_rgba / rec_tb: this lane's NR column records (tb = top | bot << 16; a column that hit
 // nothing is a "wall" of colour 0 over every row, which is what the blank picture holds).
-template <int NR>
-__device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32_t (&rec_rgba)[NR],
+// One picture quad to HBM -- and, when the engine is bound to peer gather buffers (PEERS), the
+// same quad into each peer GPU's copy over NVLink: the all-gather of the pictures happens
+// inside PAINT, store by store, instead of as a collective after the step.
+template <bool PEERS>
+__device__ __forceinline__ void solo_store(const KParams& p, uint4* o, const uint4 v) {
+  __stcs(o, v);
+  if (PEERS) {
+#pragma unroll 1
+    for (int k = 0; k < p.n_peers; ++k) *(uint4*)((char*)o + p.peer_delta[k]) = v;
+  }
+}
+template <int NR, bool PEERS>
+__device__ __forceinline__ void solo_paint(const KParams& p, uint4* __restrict__ out, const uint32_t (&rec_rgba)[NR],
                                            const uint32_t (&rec_tb)[NR], const uint32_t* __restrict__ rowsky,
                                            const uint32_t* __restrict__ rowgnd, uint32_t sky0, uint32_t gnd0, bool flat,
                                            int lane, int H) {
@@ -236,10 +247,10 @@ __device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32
       const int n = (END - j + RP - 1) / RP;                     \
       if (n > 0) {                                               \
         _Pragma("unroll 1") for (int i = 0; i < n; i += 4) {     \
-          __stcs(o + 32 * i, VAL);                               \
-          if (i + 1 < n) __stcs(o + 32 * i + 32, VAL);           \
-          if (i + 2 < n) __stcs(o + 32 * i + 64, VAL);           \
-          if (i + 3 < n) __stcs(o + 32 * i + 96, VAL);           \
+          solo_store<PEERS>(p, o + 32 * i, VAL);                               \
+          if (i + 1 < n) solo_store<PEERS>(p, o + 32 * i + 32, VAL);           \
+          if (i + 2 < n) solo_store<PEERS>(p, o + 32 * i + 64, VAL);           \
+          if (i + 3 < n) solo_store<PEERS>(p, o + 32 * i + 96, VAL);           \
         }                                                        \
         j += n * RP;                                             \
         o += 32 * n;                                             \
@@ -251,19 +262,19 @@ __device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32
       const int e2a = min(e2, e3);
 #pragma unroll 1
       for (; j < e2a; j += RP, o += 32)
-        __stcs(o, make_uint4(j < top[0] ? sky : rgba[0], j < top[1] ? sky : rgba[1], j < top[2] ? sky : rgba[2],
+        solo_store<PEERS>(p, o, make_uint4(j < top[0] ? sky : rgba[0], j < top[1] ? sky : rgba[1], j < top[2] ? sky : rgba[2],
                              j < top[3] ? sky : rgba[3]));
     }
     // (a wall of the quad ends above where another begins: all three kinds in one row)
 #define BRS_SOLO_PX(k) (j < top[k] ? sky : (j < bot[k] ? rgba[k] : gnd))
 #pragma unroll 1
-    for (; j < e2; j += RP, o += 32) __stcs(o, make_uint4(BRS_SOLO_PX(0), BRS_SOLO_PX(1), BRS_SOLO_PX(2), BRS_SOLO_PX(3)));
+    for (; j < e2; j += RP, o += 32) solo_store<PEERS>(p, o, make_uint4(BRS_SOLO_PX(0), BRS_SOLO_PX(1), BRS_SOLO_PX(2), BRS_SOLO_PX(3)));
 #undef BRS_SOLO_PX
     BRS_SOLO_RUN(e3, wallq)
     // rows where the walls end: below every top, a pixel is wall or ground
 #pragma unroll 1
     for (; j < e4; j += RP, o += 32)
-      __stcs(o, make_uint4(j < bot[0] ? rgba[0] : gnd, j < bot[1] ? rgba[1] : gnd, j < bot[2] ? rgba[2] : gnd,
+      solo_store<PEERS>(p, o, make_uint4(j < bot[0] ? rgba[0] : gnd, j < bot[1] ? rgba[1] : gnd, j < bot[2] ? rgba[2] : gnd,
                            j < bot[3] ? rgba[3] : gnd));
     BRS_SOLO_RUN(H, gndq)
 #undef BRS_SOLO_RUN
@@ -274,7 +285,7 @@ __device__ __forceinline__ void solo_paint(uint4* __restrict__ out, const uint32
       uint32_t px[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) px[k] = j < top[k] ? sky : (j < bot[k] ? rgba[k] : gnd);
-      __stcs(o, make_uint4(px[0], px[1], px[2], px[3]));
+      solo_store<PEERS>(p, o, make_uint4(px[0], px[1], px[2], px[3]));
     }
   }
 }
@@ -489,9 +500,13 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
 #ifdef BRS_SOLO_NOPAINT  // tuning experiment: everything but the picture stores (one store keeps the records alive)
       if (do_cam && lane == 0) *(uint2*)(p.cam_out + (size_t)w * (size_t)H * p.cam_w * 4) = make_uint2(rec_rgba[0] ^ rec_rgba[NR - 1], rec_tb[0] ^ rec_tb[NR - 1]);
 #else
-      if (do_cam)
-        solo_paint<NR>((uint4*)(p.cam_out + (size_t)w * (size_t)H * p.cam_w * 4), rec_rgba, rec_tb, p.row_sky, p.row_gnd,
-                       p.s_sky, p.s_gnd, p.flat_rows != 0, lane, H);
+      if (do_cam) {
+        uint4* const pic = (uint4*)(p.cam_out + (size_t)w * (size_t)H * p.cam_w * 4);
+        if (p.n_peers)
+          solo_paint<NR, true>(p, pic, rec_rgba, rec_tb, p.row_sky, p.row_gnd, p.s_sky, p.s_gnd, p.flat_rows != 0, lane, H);
+        else
+          solo_paint<NR, false>(p, pic, rec_rgba, rec_tb, p.row_sky, p.row_gnd, p.s_sky, p.s_gnd, p.flat_rows != 0, lane, H);
+      }
 #endif
     }
     // ---------------- COMMIT ------------------------------------------------------------------

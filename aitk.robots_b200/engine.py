@@ -62,6 +62,7 @@ class BatchEngine:
         self._lib = cabi.load()
         self._h = None
         self._host_allocs = []
+        self._peer_allocs, self._peer_maps = [], []
         self.scene = scene
         self.device = int(device)
         self.n_worlds = scene.n_worlds
@@ -137,6 +138,12 @@ class BatchEngine:
             for ptr in self._host_allocs:
                 self._lib.brs_host_free(self._h, ptr)
             self._host_allocs = []
+            self._lib.brs_synchronize(self._h, None)
+            for ptr in self._peer_maps:
+                self._lib.brs_peer_close(self._h, ptr)
+            for ptr in self._peer_allocs:
+                self._lib.brs_peer_free(self._h, ptr)
+            self._peer_allocs, self._peer_maps = [], []
             self._lib.brs_destroy(self._h)
             self._h = None
 
@@ -190,6 +197,32 @@ class BatchEngine:
         """Make the kernels write observation `name` straight into caller memory."""
         ptr = tensor_or_ptr if isinstance(tensor_or_ptr, int) or tensor_or_ptr is None else tensor_or_ptr.data_ptr()
         cabi.check(self._lib.brs_bind_output(self._h, _BUF_META[name][0], ptr))
+
+    def peer_alloc(self, shape, dtype):
+        """(zero-copy torch tensor, 64-byte CUDA IPC handle) of a fresh device buffer other
+        processes can map (brs_peer_alloc); freed with the engine."""
+        import torch
+
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        cabi.check(self._lib.brs_peer_alloc(self._h, n, C.byref(ptr), handle))
+        self._peer_allocs.append(ptr.value)
+        t = torch.as_tensor(_CudaBuffer(ptr.value, tuple(shape), np.dtype(dtype).str, self), device="cuda:%d" % self.device)
+        return t, bytes(handle)
+
+    def peer_open(self, handle):
+        """Device address, in this process, of a peer's brs_peer_alloc buffer (NVLink peer access)."""
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        ptr = C.c_void_p()
+        cabi.check(self._lib.brs_peer_open(self._h, buf, C.byref(ptr)))
+        self._peer_maps.append(ptr.value)
+        return ptr.value
+
+    def bind_peer_outputs(self, name, ptrs):
+        """Fused gather: observation `name` is also stored at each address of `ptrs` (peer-GPU
+        memory mapped into this process); an empty list unbinds.  See brs_bind_peer_outputs."""
+        arr = (C.c_void_p * max(len(ptrs), 1))(*[int(p) for p in ptrs])
+        cabi.check(self._lib.brs_bind_peer_outputs(self._h, _BUF_META[name][0], len(ptrs), arr))
 
     def _upload_scene(self, scene):
         B, cap = self.n_worlds, self.seg_cap

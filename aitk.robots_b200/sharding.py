@@ -64,19 +64,45 @@ class ShardedWorlds:
         self.device = torch.cuda.current_device() if device is None else device
         self.engine = BatchEngine(scene_fn(self.first, self.count), device=self.device)
         self._gather = {}
+        self._fused = set()
+        self._token = None
 
     def step(self, time_step=None, flags=7, stream=0):
         self.engine.step(time_step, flags, stream)
 
-    def gather_buffer(self, name):
+    def gather_buffer(self, name, fused=False):
         """Allocate the global observation tensor and make the kernels write this
-        rank's slice of it directly (equal shard sizes only)."""
+        rank's slice of it directly (equal shard sizes only).
+
+        fused=True (pictures of the solo launch plan): the buffer is IPC-shareable, every rank
+        maps every other rank's buffer over NVLink, and the step kernel itself stores this
+        rank's pictures into all of them (brs_bind_peer_outputs): World.step leaves the whole
+        batch on every GPU, all_gather() is then only a stream barrier across the ranks."""
+        import numpy as np
         import torch
 
         if len(set(self.counts)) != 1:
             raise ValueError("in-place gather needs equal shards; use all_gather()")
         local = self.engine.tensor(name)
-        full = torch.empty((self.n_worlds,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        shape = (self.n_worlds,) + tuple(local.shape[1:])
+        if fused and self.world_size > 1:
+            dist = _dist()
+            full, handle = self.engine.peer_alloc(shape, np.dtype(str(local.dtype).replace("torch.", "")))
+            mine_h = torch.tensor(list(handle), dtype=torch.uint8, device=local.device)
+            all_h = torch.empty((self.world_size, 64), dtype=torch.uint8, device=local.device)
+            dist.all_gather_into_tensor(all_h, mine_h, group=self.group)
+            all_h = all_h.cpu().numpy()
+            stride = int(np.prod(shape[1:])) * local.element_size()
+            ptrs = [self.engine.peer_open(bytes(all_h[r].tobytes())) + self.first * stride
+                    for r in range(self.world_size) if r != self.rank]
+            mine = full[self.first:self.first + self.count]
+            self.engine.bind_output(name, mine)
+            self.engine.bind_peer_outputs(name, ptrs)
+            self._gather[name] = (full, mine)
+            self._fused.add(name)
+            self._token = torch.zeros(1, device=local.device)
+            return full
+        full = torch.empty(shape, dtype=local.dtype, device=local.device)
         mine = full[self.first:self.first + self.count]
         self.engine.bind_output(name, mine)
         self._gather[name] = (full, mine)
@@ -84,6 +110,10 @@ class ShardedWorlds:
 
     def all_gather(self, name):
         """Observation `name` of every world on every rank."""
+        if name in self._fused:
+            # the step kernels already stored every rank's pictures everywhere: wait for all of them
+            _dist().all_reduce(self._token, group=self.group)
+            return self._gather[name][0]
         if name in self._gather:
             full, mine = self._gather[name]
             if self.world_size > 1:

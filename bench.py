@@ -549,6 +549,59 @@ def gather_measure(bench, eng, steps, name, overlap):
             "nvlink_floor_note": "(N-1) x bytes_per_rank inbound per GPU / 900 GB/s per direction (NVLink 5)"}
 
 
+def fused_gather_measure(bench, eng, steps, name="camera"):
+    """World.step with the picture all-gather INSIDE the step kernel: every rank maps every other
+    rank's gather buffer (CUDA IPC over NVLink, brs_peer_alloc / brs_peer_open) and PAINT stores
+    each picture quad locally and into all peers (brs_bind_peer_outputs).  What remains of the
+    collective is a one-element all-reduce as the cross-rank stream barrier."""
+    import numpy as np
+
+    torch, dist, rb = bench.torch, bench.dist, bench.rb
+    B, ws, rank = eng.n_worlds, bench.world_size, bench.rank
+    local = eng.tensor(name)
+    shape = (B * ws,) + tuple(local.shape[1:])
+    full, handle = eng.peer_alloc(shape, np.uint8)
+    mine_h = torch.tensor(list(handle), dtype=torch.uint8, device=local.device)
+    all_h = torch.empty((ws, 64), dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(all_h, mine_h)
+    all_h = all_h.cpu().numpy()
+    stride = int(np.prod(shape[1:]))
+    ptrs = [eng.peer_open(all_h[r].tobytes()) + rank * B * stride for r in range(ws) if r != rank]
+    mine = full[rank * B:(rank + 1) * B]
+    eng.bind_output(name, mine)
+    eng.bind_peer_outputs(name, ptrs)
+    token = torch.zeros(1, device=local.device)
+
+    def one():
+        eng.step(flags=rb.STEP_ALL, stream=bench.sh)
+        dist.all_reduce(token)  # every rank's step (and with it its stores into this GPU) is complete
+
+    for _ in range(4):
+        one()
+    bench.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(bench.stream)
+    for _ in range(steps):
+        one()
+    g1.record(bench.stream)
+    bench.barrier()
+    bench.launches += steps * eng.launch_info()["launches_per_step"]
+    # every rank must now hold every rank's pictures: compare a few remote slices with their owners'
+    probe = torch.stack([full[r * B + (B // 2)].to(torch.int64).sum() for r in range(ws)])
+    owners = [torch.zeros_like(probe) for _ in range(ws)]
+    dist.all_gather(owners, probe)
+    complete = all(int(owners[r][r]) == int(probe[r]) and int(probe[r]) > 0 for r in range(ws))
+    eng.bind_peer_outputs(name, [])
+    eng.bind_output(name, None)
+    ms, = bench.reduce([g0.elapsed_time(g1) / steps])
+    per_rank = int(mine.numel() * mine.element_size())
+    return {"observation": name, "bytes_per_rank_per_step": per_rank, "ms_per_step_with_gather": ms, "in_place": True,
+            "fused_into_step_kernel": True, "every_rank_holds_every_picture": bool(complete),
+            "nvlink_floor_ms": per_rank * (ws - 1) / 900e9 * 1e3,
+            "note": "PAINT stores each quad locally and into the (N-1) peer gather buffers over NVLink; the collective "
+                    "that remains is a one-element all-reduce as the cross-rank barrier"}
+
+
 def summarize(w):
     """Sub-object of the JSON line for one extra workload."""
     return {"workload": w["config"]["workload"], "worlds_per_gpu": w["config"]["worlds_per_gpu"],
@@ -714,9 +767,14 @@ def main():
             g_serial = gather_measure(bench, e4, steps_x, "camera", overlap=False)
             g_over = gather_measure(bench, e4, steps_x, "camera", overlap=True)
             g_small = gather_measure(bench, e4, steps_x, "pose", overlap=True)
+            try:
+                g_fused = fused_gather_measure(bench, e4, steps_x)
+            except Exception as exc:  # no peer access on this box: the NCCL numbers stand
+                g_fused = {"unavailable": str(exc)[:200]}
             if rank == 0:
                 ex["config4"]["gather_pictures"] = g_serial
                 ex["config4"]["gather_pictures_overlapped"] = g_over
+                ex["config4"]["gather_pictures_fused"] = g_fused
                 ex["config4"]["gather_poses_only"] = g_small
         e4.close()
         if rank == 0:

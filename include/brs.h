@@ -164,6 +164,24 @@ int brs_download(brs_engine* e, int which, void* host, int first_world, int n_wo
  * see that round trip). */
 int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
 
+/* The fused picture gather.  With n_peers > 0 the kernel that paints BRS_BUF_CAMERA also stores
+ * every picture at peer_ptrs[k] -- memory of another GPU mapped into this process (CUDA IPC,
+ * NVLink peer access), laid out like the engine's own camera output.  Binding, on every rank,
+ * that rank's slice of every other rank's gather buffer turns World.step into step + all-gather
+ * of the pictures in one kernel; a stream barrier across the ranks is all that remains.
+ * Supported for the solo launch plan (one robot, one camera); n_peers = 0 unbinds.  No upstream
+ * counterpart (upstream has no batch to gather). */
+int brs_bind_peer_outputs(brs_engine* e, int which, int n_peers, void* const* peer_ptrs);
+
+/* Memory for that gather: brs_peer_alloc = cudaMalloc + the allocation's CUDA IPC handle (64
+ * bytes; ship it to the other ranks with any transport), brs_peer_open = map a peer's handle
+ * into this process with NVLink peer access from this engine's GPU (cudaIpcOpenMemHandle,
+ * lazy peer access).  brs_peer_close / brs_peer_free undo them. */
+int brs_peer_alloc(brs_engine* e, size_t bytes, void** dev_ptr, unsigned char* handle64);
+int brs_peer_free(brs_engine* e, void* dev_ptr);
+int brs_peer_open(brs_engine* e, const unsigned char* handle64, void** dev_ptr);
+int brs_peer_close(brs_engine* e, void* dev_ptr);
+
 /* Seeded sensor noise (upstream: World(seed=...) seeds the sensors' noise; its model is not
  * in the mounted tree, this one is the engine's own and is mirrored by the oracle's
  * Switches.SENSOR_NOISE).  Off until called with a non-zero deviation.  Every sample is
