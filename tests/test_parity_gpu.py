@@ -539,6 +539,47 @@ def test_multi_path_step_flags():
             assert np.array_equal(x[k], y[k]), k
 
 
+def _fused_gather_worker(rank, ws, port, n_worlds):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), BRS_SOLO="1")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    from aitk_robots_b200.sharding import ShardedWorlds
+
+    sw = ShardedWorlds(lambda first, count: rb.scenes.config4(n_worlds=count, first_world=first), n_worlds, device=rank)
+    full = sw.gather_buffer("camera", fused=True)
+    for _ in range(3):
+        sw.step()
+        got = sw.all_gather("camera")
+    torch.cuda.synchronize()
+    # the reference: every rank's own pictures, gathered by NCCL from the engines' private buffers
+    mine = got[sw.first:sw.first + sw.count].clone()
+    parts = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(parts, mine)
+    assert torch.equal(torch.cat(parts, dim=0), full), "a rank does not hold every rank's pictures"
+    assert int(full[..., 3].min()) == 255
+    dist.barrier()
+    sw.engine.close()
+    dist.destroy_process_group()
+
+
+def test_fused_picture_gather_two_gpus():
+    """brs_bind_peer_outputs: the solo kernel stores its pictures into the other rank's gather
+    buffer over NVLink; after the cross-rank barrier both ranks hold the whole batch.  Needs two
+    GPUs with peer access (skipped on a one-GPU box; bench.py exercises the same path at N > 1)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_fused_gather_worker, args=(2, 29631, 64), nprocs=2, join=True)
+
+
 def test_wide_fov_camera_has_no_cone():
     """A 200-degree camera cannot use the cone cull; results still match the oracle."""
     scene = rb.scenes.config2(n_worlds=8, cam_w=64, cam_h=32)
