@@ -19,7 +19,7 @@ from .scenes import (  # noqa: F401
     SmellSpec,
 )
 from . import scenes  # noqa: F401
-from .world import Bulb, Camera, LightSensor, RangeSensor, Robot, SmellSensor, World  # noqa: F401
+from .world import Bulb, Camera, GroundCamera, LightSensor, RangeSensor, Robot, SmellSensor, World  # noqa: F401
 from .sharding import ShardedWorlds  # noqa: F401
 from .vec_env import VecEnv  # noqa: F401
 

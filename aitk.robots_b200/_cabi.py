@@ -137,6 +137,7 @@ SYMBOLS = [
     ("brs_step_host", C.c_int, [_P, C.c_double, C.c_uint, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("brs_host_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("brs_host_free", C.c_int, [_P, _P]),
+    ("brs_render_world", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     ("brs_synchronize", C.c_int, [_P, _P]),
     ("brs_count_tests", C.c_int, [_P, C.c_uint, _P, C.POINTER(C.c_ulonglong)]),
     ("brs_launch_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

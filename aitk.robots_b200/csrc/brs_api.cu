@@ -1295,6 +1295,42 @@ extern "C" int brs_host_free(brs_engine* e, void* host) {
   return BRS_OK;
 }
 
+// Top-down pictures of worlds [first, first + n): see brs_render_kernel (brs_kernels.cuh).
+extern "C" int brs_render_world(brs_engine* e, int first_world, int n_worlds, int img_w, int img_h, int robot,
+                                double view_w, double view_h, double line_px, double bulb_px, void* d_out, void* stream) {
+  if (!e || !d_out) return fail(BRS_ERR_INVALID, "brs_render_world: null argument");
+  const brs_config& c = e->cfg;
+  if (first_world < 0 || n_worlds < 1 || first_world + n_worlds > c.n_worlds || img_w < 1 || img_h < 1 || img_w > 8192 || img_h > 8192)
+    return fail(BRS_ERR_INVALID, "brs_render_world: bad world range or image size");
+  if (robot >= c.n_robots || (robot >= 0 && !(view_w > 0 && view_h > 0)))
+    return fail(BRS_ERR_INVALID, "brs_render_world: bad robot index or view size");
+  CK(cudaSetDevice(c.device));
+  RenderParams q;
+  memset(&q, 0, sizeof(q));
+  q.first_world = first_world; q.n_worlds = n_worlds; q.img_w = img_w; q.img_h = img_h;
+  q.bands = std::max(1, std::min(img_h, (4 * e->sm_count + n_worlds - 1) / n_worlds));
+  q.seg_cap = c.seg_cap; q.n_robots = c.n_robots; q.n_bulbs = c.n_bulbs;
+  q.robot = robot < 0 ? -1 : robot;
+  q.view_w = (float)view_w; q.view_h = (float)view_h;
+  q.half_px = (float)(0.5 * (line_px > 0 ? line_px : 1.5));
+  q.bulb_px = (float)(bulb_px > 0 ? bulb_px : 2.5);
+  q.ground_rgba = pack_rgb(c.ground_rgb[0], c.ground_rgb[1], c.ground_rgb[2]) | 0xff000000u;
+  q.bulb_rgba = pack_rgb(255, 255, 0) | 0xff000000u;
+  q.seg = (const uint32_t*)e->buf[BRS_BUF_SEG];
+  q.seg_count = (const int*)e->buf[BRS_BUF_SEG_COUNT];
+  q.world_size = (const float*)e->buf[BRS_BUF_WORLD_SIZE];
+  q.bulbs = (const float*)e->buf[BRS_BUF_BULBS];
+  q.pose = (const double*)e->buf[BRS_BUF_POSE];
+  q.robots = e->d_robots;
+  q.out = (uint32_t*)d_out;
+  const size_t smem = (size_t)c.seg_cap * 20 + (size_t)c.n_robots * 36 + 16;
+  if (smem > 200 * 1024) return fail(BRS_ERR_INVALID, "brs_render_world: too many walls per world for one CTA's shared memory");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void*)brs_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  brs_render_kernel<<<n_worlds * q.bands, 256, smem, (cudaStream_t)stream>>>(q);
+  CK(cudaGetLastError());
+  return BRS_OK;
+}
+
 extern "C" int brs_synchronize(brs_engine* e, void* stream) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_synchronize: null engine");
   CK(cudaSetDevice(e->cfg.device));

@@ -1832,3 +1832,121 @@ __global__ void __launch_bounds__(256) brs_fill_kernel(uint4* out, size_t n16, i
 
 #endif  // __CUDACC__
 }  // namespace brs
+
+// ------------------------------------------------------------------------------
+// Top-down renderer (upstream: the World's own picture of itself --
+// world.py display / take_picture -- and devices/cameras.py GroundCamera, the downward-looking
+// camera under a robot).  Not on the step path: a separate launch that paints the CURRENT state
+// of a range of worlds from above -- ground colour, bulbs as discs, walls as lines in list
+// order, robots as filled boxes in list order -- into RGBA images.
+//   pixel centre c = (px + 0.5, py + 0.5) looks at world point  o + c.x * u + c.y * v:
+//     whole-world view:   o = 0, u = (W / img_w, 0), v = (0, H / img_h)
+//     robot view (GroundCamera, robot >= 0): a view_w x view_h window centred on the robot,
+//       row 0 towards its front, the robot itself not drawn
+//   a wall covers the point when it is within `half` world units of the segment;
+//   a robot covers it when the point is inside its (committed) bounding box.
+// One CTA per (world, band of rows); the world's walls are staged in shared memory.  All pixel
+// arithmetic is explicit IEEE float32 (no contraction), restated in oracle/topdown.py.
+// ------------------------------------------------------------------------------
+namespace brs {
+#ifdef __CUDACC__
+struct RenderParams {
+  int first_world, n_worlds, img_w, img_h, bands, seg_cap, n_robots, n_bulbs;
+  int robot;             // < 0: whole world; else the robot the window is centred on
+  float view_w, view_h;  // robot view: window size in world units
+  float half_px;         // half line thickness, in pixels
+  float bulb_px;         // bulb disc radius, in pixels
+  uint32_t ground_rgba, bulb_rgba;
+  const uint32_t* seg;
+  const int* seg_count;
+  const float* world_size;
+  const float* bulbs;
+  const double* pose;
+  const RobotDev* robots;
+  uint32_t* out;
+};
+__global__ void __launch_bounds__(256) brs_render_kernel(const RenderParams q) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  float4* const walls = (float4*)rsm;                          // x1, y1, ex, ey
+  uint32_t* const wcol = (uint32_t*)(rsm + (size_t)q.seg_cap * 16);
+  float* const boxes = (float*)(wcol + q.seg_cap);             // per robot: 4 corners (x, y) + rgba bits
+  const int wl = blockIdx.x / q.bands, band = blockIdx.x - wl * q.bands, w = q.first_world + wl;
+  const int SC = q.seg_cap, S = min(max(q.seg_count[w], 0), SC);
+  const uint32_t* segw = q.seg + (size_t)w * 5 * SC;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const float x1 = __uint_as_float(segw[j]), y1 = __uint_as_float(segw[SC + j]);
+    walls[j] = make_float4(x1, y1, __fsub_rn(__uint_as_float(segw[2 * SC + j]), x1), __fsub_rn(__uint_as_float(segw[3 * SC + j]), y1));
+    wcol[j] = segw[4 * SC + j] | 0xff000000u;
+  }
+  for (int r = threadIdx.x; r < q.n_robots; r += blockDim.x) {
+    const double* ps = q.pose + ((size_t)w * q.n_robots + r) * 3;
+    const RobotDev& rd = q.robots[r];
+    double sn, cs;
+    sincos(ps[2], &sn, &cs);
+    for (int k = 0; k < 4; ++k) {
+      boxes[r * 9 + 2 * k] = (float)__dadd_rn(ps[0], __dsub_rn(__dmul_rn(cs, rd.cox[k]), __dmul_rn(sn, rd.coy[k])));
+      boxes[r * 9 + 2 * k + 1] = (float)__dadd_rn(ps[1], __dadd_rn(__dmul_rn(sn, rd.cox[k]), __dmul_rn(cs, rd.coy[k])));
+    }
+    boxes[r * 9 + 8] = __uint_as_float(rd.rgba | 0xff000000u);
+  }
+  __syncthreads();
+  float ox = 0.f, oy = 0.f, ux, uy = 0.f, vx = 0.f, vy;
+  if (q.robot < 0) {
+    ux = __fdiv_rn(q.world_size[2 * w], (float)q.img_w);
+    vy = __fdiv_rn(q.world_size[2 * w + 1], (float)q.img_h);
+  } else {
+    const double* ps = q.pose + ((size_t)w * q.n_robots + q.robot) * 3;
+    double sn, cs;
+    sincos(ps[2], &sn, &cs);
+    const double pu = (double)q.view_w / (double)q.img_w, pv = (double)q.view_h / (double)q.img_h;
+    const double fw = __dmul_rn(0.5 * (double)q.img_h, pv), lt = __dmul_rn(0.5 * (double)q.img_w, pu);
+    ox = (float)__dadd_rn(ps[0], __dadd_rn(__dmul_rn(cs, fw), __dmul_rn(sn, lt)));
+    oy = (float)__dadd_rn(ps[1], __dsub_rn(__dmul_rn(sn, fw), __dmul_rn(cs, lt)));
+    ux = (float)(-__dmul_rn(sn, pu));
+    uy = (float)__dmul_rn(cs, pu);
+    vx = (float)(-__dmul_rn(cs, pv));
+    vy = (float)(-__dmul_rn(sn, pv));
+  }
+  const float unit = q.robot < 0 ? fmaxf(ux, vy) : fmaxf(__fdiv_rn(q.view_w, (float)q.img_w), __fdiv_rn(q.view_h, (float)q.img_h));
+  const float half = __fmul_rn(q.half_px, unit), half2 = __fmul_rn(half, half);
+  const float br = __fmul_rn(q.bulb_px, unit), br2 = __fmul_rn(br, br);
+  const int rows = (q.img_h + q.bands - 1) / q.bands, r0 = band * rows, r1 = min(r0 + rows, q.img_h);
+  uint32_t* img = q.out + (size_t)wl * q.img_h * q.img_w;
+  for (int i = r0 * q.img_w + threadIdx.x; i < r1 * q.img_w; i += blockDim.x) {
+    const int py = i / q.img_w, px = i - py * q.img_w;
+    const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
+    const float x = __fadd_rn(ox, __fadd_rn(__fmul_rn(cx, ux), __fmul_rn(cy, vx)));
+    const float y = __fadd_rn(oy, __fadd_rn(__fmul_rn(cx, uy), __fmul_rn(cy, vy)));
+    uint32_t c = q.ground_rgba;
+    for (int b = 0; b < q.n_bulbs; ++b) {
+      const float* bl = q.bulbs + ((size_t)w * q.n_bulbs + b) * 4;
+      const float dx = __fsub_rn(x, bl[0]), dy = __fsub_rn(y, bl[1]);
+      if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= br2) c = q.bulb_rgba;
+    }
+    for (int j = 0; j < S; ++j) {
+      const float4 s = walls[j];
+      const float dx = __fsub_rn(x, s.x), dy = __fsub_rn(y, s.y);
+      const float ee = __fadd_rn(__fmul_rn(s.z, s.z), __fmul_rn(s.w, s.w));
+      float h = ee > 0.f ? __fdiv_rn(__fadd_rn(__fmul_rn(dx, s.z), __fmul_rn(dy, s.w)), ee) : 0.f;
+      h = fminf(fmaxf(h, 0.f), 1.f);
+      const float wx = __fsub_rn(dx, __fmul_rn(h, s.z)), wy = __fsub_rn(dy, __fmul_rn(h, s.w));
+      if (__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)) <= half2) c = wcol[j];
+    }
+    for (int r = 0; r < q.n_robots; ++r) {
+      if (r == q.robot) continue;
+      const float* bx = boxes + r * 9;
+      bool pos = true, neg = true;
+      for (int k = 0; k < 4; ++k) {
+        const int k2 = (k + 1) & 3;
+        const float ex = __fsub_rn(bx[2 * k2], bx[2 * k]), ey = __fsub_rn(bx[2 * k2 + 1], bx[2 * k + 1]);
+        const float cr = __fsub_rn(__fmul_rn(ex, __fsub_rn(y, bx[2 * k + 1])), __fmul_rn(ey, __fsub_rn(x, bx[2 * k])));
+        pos = pos && cr >= 0.f;
+        neg = neg && cr <= 0.f;
+      }
+      if (pos || neg) c = __float_as_uint(bx[8]);
+    }
+    img[i] = c;
+  }
+}
+#endif
+}  // namespace brs

@@ -218,6 +218,23 @@ class BatchEngine:
         self._peer_maps.append(ptr.value)
         return ptr.value
 
+    def render_world(self, first_world=0, n_worlds=None, width=256, height=None, robot=-1, view=None, line_px=0.0,
+                     bulb_px=0.0, stream=0):
+        """Top-down RGBA pictures [n, height, width, 4] (torch uint8, on the device) of the
+        worlds' current state (brs_render_world).  ``robot`` >= 0 with ``view=(w, h)`` in world
+        units: the window under / around that robot, row 0 towards its front (GroundCamera)."""
+        import torch
+
+        n = self.n_worlds - first_world if n_worlds is None else n_worlds
+        if height is None:
+            ws = self.scene.world_size[first_world] if view is None else view
+            height = max(1, int(round(width * float(ws[1]) / float(ws[0]))))
+        vw, vh = (0.0, 0.0) if view is None else (float(view[0]), float(view[1]))
+        out = torch.empty((n, height, width, 4), dtype=torch.uint8, device="cuda:%d" % self.device)
+        cabi.check(self._lib.brs_render_world(self._h, int(first_world), int(n), int(width), int(height), int(robot),
+                                              vw, vh, float(line_px), float(bulb_px), out.data_ptr(), stream))
+        return out
+
     def bind_peer_outputs(self, name, ptrs):
         """Fused gather: observation `name` is also stored at each address of `ptrs` (peer-GPU
         memory mapped into this process); an empty list unbinds.  See brs_bind_peer_outputs."""

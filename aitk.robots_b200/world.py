@@ -116,6 +116,32 @@ class Camera(_Device):
     get_image = take_picture
 
 
+class GroundCamera(_Device):
+    """Downward-looking camera (upstream devices/cameras.py GroundCamera [RECALL]): a
+    ``width`` x ``height`` pixel picture of the ``view`` (world units) window centred on the
+    robot, row 0 towards its front; the robot itself is not in it.  Painted by the engine's
+    top-down renderer (brs_render_world) from the current state -- no per-step cost."""
+
+    def __init__(self, width=15, height=15, view=None, name="ground-camera"):
+        super().__init__()
+        self.width, self.height = int(width), int(height)
+        self.view = (float(width), float(height)) if view is None else (float(view[0]), float(view[1]))
+        self.name = name
+        self.spec = None  # nothing for the step kernels to do
+
+    def take_picture(self, as_array=False):
+        w = self._world()
+        w._ensure_engine()
+        img = w._engine.render_world(0, 1, self.width, self.height, robot=self.robot._slot, view=self.view)[0].cpu().numpy()
+        if as_array:
+            return img
+        from PIL import Image
+
+        return Image.fromarray(img, "RGBA")
+
+    get_image = take_picture
+
+
 class LightSensor(_Device):
     def __init__(self, position=(0, 0), name="light"):
         super().__init__()
@@ -249,7 +275,7 @@ class Robot:
     def _spec(self):
         return RobotSpec(bbox=self.bbox, height=self.height, rgba=self.color,
                          max_trans_velocity=self.max_trans_velocity, max_rotate_velocity=self.max_rotate_velocity,
-                         devices=[d.spec for d in self._devices])
+                         devices=[d.spec for d in self._devices if d.spec is not None])
 
 
 class World:
@@ -381,7 +407,7 @@ class World:
         if self._engine is not None:
             carry = (self._engine.download("vel"), self._engine.download("stalled"))
             self._engine.close()
-        idx = {RangeSensor: 0, Camera: 0, LightSensor: 0, SmellSensor: 0}
+        idx = {RangeSensor: 0, Camera: 0, LightSensor: 0, SmellSensor: 0, GroundCamera: 0}
         for r in self._robots:
             for d in r._devices:
                 d._index = idx[type(d)]
@@ -438,6 +464,22 @@ class World:
         self._engine.step(self.time_step, cabi.STEP_CAMERA)
         return self._engine.download("camera")
 
+    def take_picture(self, width=None, height=None, as_array=False):
+        """The world from above as it is now (upstream World.take_picture / display [RECALL]):
+        ground, bulbs, walls, robots -- painted by the engine (brs_render_world).  Default
+        size: one pixel per world unit, at most 1024 wide."""
+        self._ensure_engine()
+        if width is None:
+            width = int(min(1024, max(1, round(self.width))))
+        img = self._engine.render_world(0, 1, int(width), None if height is None else int(height))[0].cpu().numpy()
+        if as_array:
+            return img
+        from PIL import Image
+
+        return Image.fromarray(img, "RGBA")
+
+    get_image = take_picture
+
     # -- stepping --------------------------------------------------------------------
     def step(self, time_step=None):
         """One tick: move every robot, refresh every device, advance the clock."""
@@ -473,6 +515,10 @@ class World:
             x, y, a = r.get_pose()
             devs = []
             for d in r._devices:
+                if isinstance(d, GroundCamera):
+                    devs.append({"class": "GroundCamera", "width": d.width, "height": d.height,
+                                 "view": list(d.view), "name": d.name})
+                    continue
                 spec = dict(vars(d.spec))
                 spec["position"] = list(spec["position"])
                 spec["class"] = type(d).__name__
@@ -510,7 +556,8 @@ class World:
             world.add_bulb(b["color"], b["x"], b["y"], b.get("z", 0.0), b.get("brightness", 1.0), b.get("name", "bulb"))
         for f in config.get("food", []):
             world.add_food(*f)
-        kinds = {"RangeSensor": RangeSensor, "Camera": Camera, "LightSensor": LightSensor, "SmellSensor": SmellSensor}
+        kinds = {"RangeSensor": RangeSensor, "Camera": Camera, "LightSensor": LightSensor, "SmellSensor": SmellSensor,
+                 "GroundCamera": GroundCamera}
         for rc in config.get("robots", []):
             robot = Robot(rc["x"], rc["y"], rc["a"], color=rc.get("color", "red"), name=rc.get("name", "Robbie"),
                           height=rc.get("height", 0.25), max_trans_velocity=rc.get("max_trans_velocity", 2.0),

@@ -221,6 +221,20 @@ int brs_step_host(brs_engine* e, double time_step, unsigned flags,
 int brs_host_alloc(brs_engine* e, size_t bytes, void** host);
 int brs_host_free(brs_engine* e, void* host);
 
+/* Top-down pictures of worlds [first_world, first_world + n_worlds) in their CURRENT state
+ * (upstream world.py: the World's picture of itself -- display / take_picture; upstream
+ * devices/cameras.py GroundCamera: the downward camera under a robot.  The exact look is not in
+ * the mounted tree; this is the engine's own definition, restated in oracle/topdown.py):
+ * RGBA [n_worlds][img_h][img_w][4] into device memory `d_out`.
+ *   robot < 0:  pixel (px, py) looks at world point ((px + .5) W / img_w, (py + .5) H / img_h);
+ *   robot >= 0: a view_w x view_h window (world units) centred on that robot, row 0 towards its
+ *               front, the robot itself not drawn.
+ * Ground colour, bulbs as discs of bulb_px pixels radius, walls as lines line_px pixels thick in
+ * list order, robots as filled boxes in list order (0 = defaults 1.5 / 2.5).  Not part of
+ * brs_step: a separate launch on `stream`. */
+int brs_render_world(brs_engine* e, int first_world, int n_worlds, int img_w, int img_h, int robot, double view_w,
+                     double view_h, double line_px, double bulb_px, void* d_out, void* stream);
+
 /* Block the calling host thread until `stream` has drained. */
 int brs_synchronize(brs_engine* e, void* stream);
 

@@ -195,3 +195,28 @@ def test_philox4x32_10_known_answers():
     m = sum(zs) / len(zs)
     sd = (sum((z - m) ** 2 for z in zs) / len(zs)) ** 0.5
     assert abs(m) < 0.06 and abs(sd - 1.0) < 0.05, (m, sd)
+
+
+def test_topdown_restatement_known_pixels():
+    """oracle/topdown.py: hand-checkable picture (one wall, one bulb, one robot)."""
+    import numpy as np
+
+    from oracle import topdown
+
+    seg = np.zeros((4, 4), dtype=np.float32)
+    seg[:, 0] = (10, 10, 90, 10)
+    rgba = np.zeros((4, 4), dtype=np.uint8)
+    rgba[0] = (0, 0, 255, 7)
+    poses = np.array([[50.0, 30.0, 0.0]])
+    img, fragile = topdown.render((100, 50), seg, rgba, 1, poses, [(-7.5, 7.5, -6.67, 6.67)], [(255, 0, 0, 255)],
+                                  bulbs=[(20, 40, 0, 1)], img_w=100, img_h=50)
+    assert tuple(img[10, 50]) == (0, 0, 255, 255) and tuple(img[9, 50]) == (0, 0, 255, 255)  # line 1.5 px thick
+    assert tuple(img[12, 50]) == (0, 128, 0, 255)
+    assert tuple(img[30, 50]) == (255, 0, 0, 255) and tuple(img[30, 58]) == (0, 128, 0, 255)
+    assert tuple(img[40, 20]) == (255, 255, 0, 255)
+    assert not fragile.all()
+    # the window under the robot: robot not drawn, wall 20 units to its left (heading 0 = +x, wall is at -y)
+    img, _ = topdown.render((100, 50), seg, rgba, 1, poses, [(-7.5, 7.5, -6.67, 6.67)], [(255, 0, 0, 255)],
+                            img_w=50, img_h=50, robot=0, view=(50.0, 50.0))
+    assert tuple(img[25, 25]) == (0, 128, 0, 255)
+    assert tuple(img[25, 5]) == (0, 0, 255, 255) and tuple(img[25, 45]) == (0, 128, 0, 255)

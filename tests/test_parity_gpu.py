@@ -854,3 +854,61 @@ def test_very_wide_camera_and_sky_gradient():
         assert len(np.unique(cam[0, 0, :3, :, 2])) > 1  # the sky really is a gradient
     finally:
         orc.SW.CAMERA_SKY_GRAD, orc.SW.CAMERA_GROUND_GRAD = old
+
+
+@pytest.mark.parametrize("maker,size", [
+    (lambda: rb.scenes.demo_scene(6), (240, 180)),
+    (lambda: rb.scenes.config4(n_worlds=5), (200, 117)),
+    (lambda: rb.scenes.config3(n_worlds=4), (97, 64)),
+])
+def test_topdown_renderer_matches_the_restatement(maker, size):
+    """brs_render_world (whole-world view and the GroundCamera window under a robot) against
+    oracle/topdown.py, pixel for pixel, after the robots have moved."""
+    from oracle import topdown
+
+    scene = maker()
+    eng = rb.BatchEngine(scene)
+    for _ in range(3):
+        eng.step()
+    poses = eng.download("pose")
+    W, H = size
+    img = eng.render_world(0, None, W, H).cpu().numpy()
+    assert img.shape == (scene.n_worlds, H, W, 4)
+    gv = eng.render_world(1, scene.n_worlds - 1, 40, 30, robot=0, view=(60.0, 45.0)).cpu().numpy()
+    total = bad = fragile_n = 0
+    for i in range(scene.n_worlds):
+        ref, fragile = topdown.render_scene_world(scene, i, poses[i], img_w=W, img_h=H)
+        diff = (img[i] != ref).any(axis=-1)
+        assert not (diff & ~fragile).any(), (i, np.argwhere(diff & ~fragile)[:5])
+        total, bad, fragile_n = total + diff.size, bad + int(diff.sum()), fragile_n + int(fragile.sum())
+        assert len(np.unique(ref.reshape(-1, 4), axis=0)) >= 3  # ground, walls, a robot: not a blank picture
+        if i >= 1:
+            ref, fragile = topdown.render_scene_world(scene, i, poses[i], img_w=40, img_h=30, robot=0, view=(60.0, 45.0))
+            diff = (gv[i - 1] != ref).any(axis=-1)
+            assert not (diff & ~fragile).any(), (i, np.argwhere(diff & ~fragile)[:5])
+            total, bad, fragile_n = total + diff.size, bad + int(diff.sum()), fragile_n + int(fragile.sum())
+    assert bad <= 1e-3 * total and fragile_n <= 0.02 * total, (bad, fragile_n, total)
+    eng.close()
+
+
+def test_facade_world_picture_and_ground_camera():
+    w = rb.World(200, 100)
+    w.add_wall("blue", 50, 20, 60, 80)
+    r = rb.Robot(100, 50, 0, color="red")
+    g = r.add_device(rb.GroundCamera(width=20, height=20, view=(40, 40)))
+    r.add_device(rb.RangeSensor(position=(8, 0), a=0, max=50, width=0))
+    w.add_robot(r)
+    w.step()
+    pic = w.take_picture(as_array=True)
+    assert pic.shape == (100, 200, 4)
+    assert tuple(pic[50, 100]) == (255, 0, 0, 255)   # the robot
+    assert tuple(pic[50, 55]) == (0, 128, 0, 255)    # inside the box wall: ground
+    assert tuple(pic[50, 50]) == (0, 0, 255, 255)    # its left edge
+    assert tuple(pic[5, 150]) == (0, 128, 0, 255)
+    gp = g.take_picture(as_array=True)
+    assert gp.shape == (20, 20, 4) and (gp.reshape(-1, 4) == (0, 128, 0, 255)).all()  # robot not in its own view
+    r.set_pose(72, 50, 180)  # now facing the wall's right edge at x = 60: 12 units ahead
+    gp = g.take_picture(as_array=True)
+    assert tuple(gp[3, 10]) == (0, 0, 255, 255) and tuple(gp[15, 10]) == (0, 128, 0, 255)
+    w2 = rb.World.from_json(w.to_json())
+    assert isinstance(list(w2)[0][0], rb.GroundCamera) and list(w2)[0][0].view == (40.0, 40.0)
