@@ -62,9 +62,12 @@ struct brs_engine {
   uint32_t* d_rowgnd = nullptr;
   int flat_rows = 1;
   unsigned int* d_sched = nullptr;
+  unsigned int* d_epoch = nullptr;  // [n_tiles][2] brs_steps on the fused kernel: per-tile epochs (committed, painted)
+  unsigned epoch0 = 0;              // every epoch word is <= epoch0 between launches
   unsigned long long* d_phase = nullptr;  // BRS_PHASE_TIMING builds
   unsigned long long* d_counters = nullptr;  // [2] executed-work counters (brs_step_counted)
   bool counting = false;
+  bool steps_off = false;  // BRS_STEPS_ONE_LAUNCH=0: brs_steps always launches once per step
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
@@ -839,6 +842,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   }
   // ---- brs_step_host pipeline: a copy stream and the events that chain it to the caller's
   e->host_chunks = std::max(1, std::min(8, env_int("BRS_HOST_CHUNKS", cfg->n_worlds >= 8192 ? 4 : 1)));
+  e->steps_off = env_int("BRS_STEPS_ONE_LAUNCH", 1) == 0;
   ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
   for (int k = 0; k < 8 && ce == cudaSuccess; ++k) ce = cudaEventCreateWithFlags(&e->ev_chunk[k], cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming);
@@ -881,6 +885,7 @@ extern "C" int brs_destroy(brs_engine* e) {
   cudaFree(e->d_gr_idx);
   cudaFree(e->d_dr_idx);
   cudaFree(e->d_sched);
+  cudaFree(e->d_epoch);
   cudaFree(e->d_camcs);
   cudaFree(e->d_rowsky);
   cudaFree(e->d_rowgnd);
@@ -1083,6 +1088,7 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
   p.groups = e->d_groups; p.gr_idx = e->d_gr_idx; p.dr_idx = e->d_dr_idx;
   p.cam_cs = e->d_camcs; p.row_sky = e->d_rowsky; p.row_gnd = e->d_rowgnd;
   p.sched = e->d_sched;
+  p.epoch = e->d_epoch;
   p.phase = e->d_phase;
   p.wsg = e->d_ws;
   p.counters = e->counting ? e->d_counters : nullptr;
@@ -1109,9 +1115,11 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
 
 // One World.step over worlds [first, first + n): every buffer has `world` as its leading
 // dimension, so a sub-range is the same kernel on shifted base pointers.
-static int launch_range(brs_engine* e, int first, int n, double time_step, unsigned flags, void* stream) {
+static int launch_range(brs_engine* e, int first, int n, double time_step, unsigned flags, void* stream, int n_steps = 1) {
   KParams p;
   fill_params(e, p, time_step, flags, e->wide);
+  p.n_steps = n_steps;
+  p.epoch0 = e->epoch0;
   const brs_config& c = e->cfg;
   int grid = e->solo ? e->s_grid : e->wide ? e->w_grid : e->grid;
   if (first != 0 || n != c.n_worlds) {
@@ -1166,6 +1174,60 @@ extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* s
   const int rc = launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream);
   if (flags & BRS_STEP_SENSE) ++e->noise_step;
   return rc;
+}
+
+// World.steps(n): n consecutive steps with the inputs as they are now.  One launch when the
+// active plan can carry its pipeline across step boundaries (fused, solo, solo range; every
+// tile / world then belongs to one CTA / warp for the whole launch), else n launches.  Every
+// step writes all of its observations; what is left in the buffers is the last step's.
+static bool steps_one_launch(const brs_engine* e, unsigned flags, int n_steps) {
+  return n_steps > 1 && (flags & BRS_STEP_MOVE) && !e->noise.on && !e->counting && !e->wide && !e->prep_fused &&
+         !e->multi && !e->steps_off;
+}
+// (the fused kernel counts (step, tile) items in 32 bits: very long runs go in pieces)
+static int steps_piece(const brs_engine* e, int n_steps) {
+  const int tiles = e->solo ? 1 : std::max(e->n_tiles, 1);
+  return std::max(2, (int)std::min<long long>(n_steps, 0x3fffffffll / tiles));
+}
+extern "C" int brs_steps_launches(brs_engine* e, unsigned flags, int n_steps, int* launches) {
+  if (!e || !launches) return fail(BRS_ERR_INVALID, "brs_steps_launches: null argument");
+  const int per = (e->wide || e->prep_fused) ? 2 : 1;
+  if (!(flags & BRS_STEP_ALL) || n_steps <= 0) *launches = 0;
+  else if (steps_one_launch(e, flags, n_steps)) *launches = (n_steps + steps_piece(e, n_steps) - 1) / steps_piece(e, n_steps);
+  else *launches = ((flags & BRS_STEP_MOVE) ? n_steps : 1) * per;
+  return BRS_OK;
+}
+extern "C" int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_steps, void* stream) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_steps: null engine");
+  if (n_steps < 0) return fail(BRS_ERR_INVALID, "brs_steps: n_steps < 0");
+  if (!(flags & BRS_STEP_ALL) || n_steps == 0) return BRS_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const bool one_launch = steps_one_launch(e, flags, n_steps);
+  if (one_launch) {
+    const int tiles = e->solo ? 1 : std::max(e->n_tiles, 1);
+    const int piece = steps_piece(e, n_steps);
+    for (int done = 0; done < n_steps;) {
+      const int n = std::min(piece, n_steps - done);
+      if (!e->solo && !e->d_epoch) {
+        CK(cudaMalloc((void**)&e->d_epoch, (size_t)tiles * 8));
+        CK(cudaMemsetAsync(e->d_epoch, 0, (size_t)tiles * 8, (cudaStream_t)stream));
+        e->epoch0 = 0;
+        e->kp_flags = 0xffffffffu;  // the cached parameters carry the pointer
+      }
+      const int rc = launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream, n);
+      if (rc) return rc;
+      if (!e->solo && n > 1) e->epoch0 += (unsigned)n;
+      done += n;
+    }
+    return BRS_OK;
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    const int rc = launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream);
+    if (flags & BRS_STEP_SENSE) ++e->noise_step;
+    if (rc) return rc;
+    if (!(flags & BRS_STEP_MOVE)) break;  // sensing a world that does not move twice is sensing it once
+  }
+  return BRS_OK;
 }
 
 // Seeded sensor noise.  Off by default (the parity contract of BASELINE.json is stated with

@@ -203,6 +203,15 @@ struct KParams {
   // fused / wide paths, direct-path range sensors: per (world, robot) lists of the segments within
   // m_reach of the robot (shared memory behind the kernel's own layout; 0 = search every segment)
   int use_rlist, rl_off, rc_off;
+  // brs_steps: this launch runs n_steps consecutive World.steps (0 / 1 = one).  A tile (fused
+  // kernel) or a world (solo kernel) belongs to ONE CTA / warp for the whole launch -- static
+  // assignment, no tile counter -- so step s+1 of a world only ever follows step s of the same
+  // world in program order, and the pipelines run on across the step boundaries.
+  int n_steps;
+  // fused kernel under brs_steps: [n_tiles][2] epoch words (committed, painted), both equal to
+  // epoch0 or less when the launch starts; the host advances epoch0 by n_steps per launch
+  unsigned* epoch;
+  unsigned epoch0;
 };
 
 // per-column paint record
@@ -265,7 +274,7 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
   L.cpar = o;  // (the collision disc moved into the ws record, BRS_WS_CPAR)
   L.cq = o; o += 4 * 256;  // collision candidate queue: count + BRS_CQ_MAX packed (robot item, wall)
   L.mbar = o; o += 2 * 8;
-  L.sched = o; o += 16;
+  L.sched = o; o += 32;  // [1..2] tile per buffer; brs_steps: [3..4] outputs free?, [5..6] else the epoch to wait for
   L.total = align_up(o, 16);
   return L;
 }
@@ -384,6 +393,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
+}
+// epoch words between CTAs (brs_steps).  The writer publishes with a release store (prior
+// writes of the CTA, ordered before it by the barrier, are visible at L2 first).  The reader
+// polls with a RELAXED load and reads the state the epoch guards -- poses, velocities -- with
+// L2 loads (ld_state: ld.relaxed.gpu, never served from the SM's L1), issued after a barrier
+// that follows the poll: an acquire load would do the same job by invalidating the whole L1
+// of the SM on every tile (SASS: CCTL.IVALL), which costs the other CTAs of the SM their
+// cached descriptors and tables (measured: config 3 10 % slower).
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* a) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* a, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_state(const double* a) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(a) : "memory");
+  return v;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
@@ -867,8 +896,9 @@ __device__ __forceinline__ void prep_robot_half(const KParams& p, int w, int r, 
   const int R = p.n_robots;
   const RobotDev& rd = p.robots[r];
   const size_t o = ((size_t)w * R + r) * 3;
-  const double x = p.pose[o], y = p.pose[o + 1], a = p.pose[o + 2];
-  const double v0 = p.vel[o], v1 = p.vel[o + 1], v2 = p.vel[o + 2];
+  // (the state a previous step wrote, possibly on another SM under brs_steps: L2 loads)
+  const double x = ld_state(p.pose + o), y = ld_state(p.pose + o + 1), a = ld_state(p.pose + o + 2);
+  const double v0 = ld_state(p.vel + o), v1 = ld_state(p.vel + o + 1), v2 = ld_state(p.vel + o + 2);
   double vx = v0, vy = v1, va = v2, pa = a;
   if (prop) {
     const double* tv = p.tvel + o;
@@ -1727,6 +1757,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
   BRS_PH_DECL;
   // iteration -1 only lets the helper team step the CTA's first tile
   int tile = 0;
+  int h_prev1 = -1, h_prev2 = -1;  // brs_steps (scheduler thread): items of the last two iterations, to be published
   for (int it = -1;; ++it) {
     const int buf = it & 1;
     const int w0 = tile * TW, nw = min(TW, p.n_worlds - w0);
@@ -1736,7 +1767,50 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
         // next tile index + TMA of its wall store into the other buffer (free since the
         // barrier that ended the previous iteration)
         // (the first tile of a CTA is its block index; the counter hands out the rest)
-        const int tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
+        int tn;
+        if (p.n_steps > 1) {
+          // brs_steps: the counter hands out n_steps * n_tiles items in (step, tile) order.  Step s
+          // of a tile may run on another CTA than its step s-1, so two epoch words per tile order
+          // them: `committed` (poses, velocities, stall flags of the tile are those after step s)
+          // gates the helper, `painted` (every observation of step s is written) gates the
+          // workers' stores.  Both are published here, by this thread, after the barrier that
+          // ended the iteration which produced them.  A waiter's item is always later in item
+          // order than what it waits for, and every CTA of the grid is resident: no deadlock.
+          // (a batch of no more tiles than CTAs: CTA b keeps tile b for every step -- program
+          // order does the rest, no counter, no epochs; config 1 as written is this case)
+          const bool own = p.n_tiles <= (int)gridDim.x;
+          unsigned* const ep = p.epoch;
+          if (own) {
+            tn = ((int)blockIdx.x < p.n_tiles && it + 1 < p.n_steps) ? (int)blockIdx.x : p.n_tiles;
+            sched[3 + (buf ^ 1)] = 1;
+          } else {
+          if (h_prev1 >= 0) st_release_gpu(ep + 2 * (h_prev1 % p.n_tiles), p.epoch0 + (unsigned)(h_prev1 / p.n_tiles) + 1u);
+          if (h_prev2 >= 0) st_release_gpu(ep + 2 * (h_prev2 % p.n_tiles) + 1, p.epoch0 + (unsigned)(h_prev2 / p.n_tiles) + 1u);
+          // (every item comes from the counter, the first one too: a CTA that is not resident yet owns nothing)
+          const long long k = (long long)atomicAdd(&p.sched[0], 1u);
+          int ok = 1;
+          unsigned want = 0;
+          if (k < (long long)p.n_steps * p.n_tiles) {
+            tn = (int)(k % p.n_tiles);
+            const unsigned sk = (unsigned)(k / p.n_tiles);
+            if (sk > 0) {
+              want = p.epoch0 + sk;
+              while ((int)(ld_relaxed_gpu(ep + 2 * tn) - want) < 0) __nanosleep(64);
+              ok = (int)(ld_relaxed_gpu(ep + 2 * tn + 1) - want) >= 0;
+            }
+            h_prev2 = h_prev1;
+            h_prev1 = (int)k;
+          } else {
+            tn = p.n_tiles;
+            h_prev2 = h_prev1;
+            h_prev1 = -1;
+          }
+          sched[3 + (buf ^ 1)] = ok;
+          sched[5 + (buf ^ 1)] = (int)want;
+          }
+        } else {
+          tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
+        }
         sched[1 + (buf ^ 1)] = tn;
         if ((!BIG || p.prepped) && tn < p.n_tiles) {
           const int wn = tn * TW, nn = min(TW, p.n_worlds - wn);
@@ -1773,6 +1847,15 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       const GroupCull* const gcull = (const GroupCull*)(smem + L.gcull[buf]);
       // every thread observes the phase of this tile's wall store itself before reading it
       if (!BIG || p.prepped) mbar_wait(smem_u32(&mbar[buf]), (uint32_t)(it >> 1) & 1u);
+      if (p.n_steps > 1 && !sched[3 + buf]) {
+        // brs_steps: the previous step's observations of this tile were still being written by
+        // another CTA when the item was fetched (rare: the same tile comes up n_tiles items later)
+        if (tid == 0) {
+          const unsigned want = (unsigned)sched[5 + buf];
+          while ((int)(ld_relaxed_gpu(p.epoch + 2 * tile + 1) - want) < 0) __nanosleep(64);
+        }
+        team_sync(1, NW);
+      }
       BRS_PH(tid == 0, 0);
 
       sense_paint_tile<NR>(p, tid, NW, lane, w0, nw, do_sense, do_cam, !p.direct_on_helper, rawb, segtab, wsb, meta, org,
@@ -1786,6 +1869,10 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
     BRS_PH(tid == NW, 15);
   }
 
+  // brs_steps: the observations of the CTA's last item (its poses were published at the top of
+  // the last iteration); the scheduler thread holds the item in h_prev2 after fetching the sentinel
+  if (p.n_steps > 1 && tid == NW && h_prev2 >= 0 && p.n_tiles > (int)gridDim.x)
+    st_release_gpu(p.epoch + 2 * (h_prev2 % p.n_tiles) + 1, p.epoch0 + (unsigned)(h_prev2 / p.n_tiles) + 1u);
   // self-resetting scheduler: the last CTA to leave zeroes both counters for the next launch
   if (tid == 0) {
     __threadfence();

@@ -346,6 +346,10 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
   for (int k = 0; k < NR; ++k) ccs[k] = do_cam ? p.cam_cs[lane * NR + k] : make_double2(0.0, 0.0);
   uint32_t parity = 0;
 
+  // brs_steps: the warp runs its worlds n_steps times over; step s+1 of a world follows its
+  // step s in this warp's program order, the wall copies run on across the boundary
+  const int nst = max(p.n_steps, 1);
+  for (int st = 0; st < nst; ++st)
   for (int b0 = 0; b0 < cnt; b0 += BRS_SOLO_BATCH) {
     const int nb = min(BRS_SOLO_BATCH, cnt - b0);
     // ---------------- PREP ----------------------------------------------------------------
@@ -492,9 +496,10 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_solo_kernel(const __grid_con
       // every lane is done with this world's walls: request the next world's while the
       // picture is written
       __syncwarp();
-      if (lane == 0 && b0 + k + 1 < cnt) {
+      if (lane == 0 && (b0 + k + 1 < cnt || st + 1 < nst)) {
+        const int wnext = b0 + k + 1 < cnt ? w + wstr : wbeg;
         mbar_expect_tx(bar, world_bytes);
-        tma_bulk_g2s(smem_u32(raw), p.seg + (size_t)(w + wstr) * 5 * SC, world_bytes, bar);
+        tma_bulk_g2s(smem_u32(raw), p.seg + (size_t)wnext * 5 * SC, world_bytes, bar);
       }
       // ---------------- PAINT -----------------------------------------------------------------
 #ifdef BRS_SOLO_NOPAINT  // tuning experiment: everything but the picture stores (one store keeps the records alive)
@@ -617,6 +622,8 @@ __global__ void __launch_bounds__(NT, MIN_CTAS) brs_scan_kernel(const __grid_con
   const int g = lane & (SL - 1), rbase = lane / SL, rstep = 32 / SL;
   const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
 
+  const int nst = max(p.n_steps, 1);  // brs_steps: see brs_solo_kernel
+  for (int st = 0; st < nst; ++st)
   for (int b0 = 0; b0 < cnt; b0 += BRS_SOLO_BATCH) {
     const int nb = min(BRS_SOLO_BATCH, cnt - b0);
     // ---------------- PREP ----------------------------------------------------------------

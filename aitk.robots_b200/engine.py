@@ -263,6 +263,18 @@ class BatchEngine:
         dt = self.time_step if time_step is None else time_step
         cabi.check(self._lib.brs_step(self._h, float(dt), int(flags), stream))
 
+    def steps(self, n, time_step=None, flags=cabi.STEP_ALL, stream=0):
+        """World.steps(n) over the whole batch: n consecutive steps with the current target
+        velocities, in ONE launch where the plan allows (brs_steps); bit-identical to n step()s."""
+        dt = self.time_step if time_step is None else time_step
+        cabi.check(self._lib.brs_steps(self._h, float(dt), int(flags), int(n), stream))
+
+    def steps_launches(self, n, flags=cabi.STEP_ALL):
+        """Kernel launches steps(n, flags) issues on this engine as it is configured now."""
+        k = C.c_int()
+        cabi.check(self._lib.brs_steps_launches(self._h, int(flags), int(n), C.byref(k)))
+        return int(k.value)
+
     def step_host(self, time_step=None, flags=cabi.STEP_ALL, target_vel=0, pose=0, stalled=0, range_=0, camera=0,
                   light=0, smell=0, stream=0):
         """The same step with HOST (pinned) buffers given as raw addresses (0 = skip)."""

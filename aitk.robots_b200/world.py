@@ -498,8 +498,19 @@ class World:
         self._pull_obs()
 
     def steps(self, n, time_step=None):
-        for _ in range(int(n)):
-            self.step(time_step)
+        """n ticks with the robots' current move() commands (upstream World.steps): one engine
+        call (brs_steps), state and observations read back once at the end."""
+        n = int(n)
+        if n <= 0:
+            return
+        self._ensure_engine()
+        dt = self.time_step if time_step is None else time_step
+        self._engine.upload("target_vel", np.array([[r._tvel for r in self._robots]], dtype=np.float64))
+        self._engine.steps(n, dt, cabi.STEP_MOVE | cabi.STEP_SENSE)
+        for _ in range(n):
+            self.time = round(self.time + dt, 10)
+        self._pull_state()
+        self._pull_obs()
 
     # -- scene files (SURVEY.md section 8(f), rank 2) ---------------------------------
     def to_json(self):

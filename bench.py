@@ -356,6 +356,24 @@ class Bench:
         total = evs[0].elapsed_time(evs[-1])
         return total, ([evs[k].elapsed_time(evs[k + 1]) for k in range(steps)] if per_launch else None)
 
+    def time_steps_call(self, eng, flags, steps, warmup):
+        """The same K steps as ONE call of brs_steps (upstream World.steps(K): K consecutive
+        steps, every one writing all its observations; one launch where the plan allows, the
+        pipeline running on across the step boundaries).  Returns (total ms, launches)."""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            eng.step(flags=flags, stream=self.sh)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        eng.steps(steps, flags=flags, stream=self.sh)
+        e1.record(self.stream)
+        self.barrier()
+        n = eng.steps_launches(steps, flags)
+        self.launches += n
+        return e0.elapsed_time(e1), n
+
     def rooflines(self, eng, ms, tests_per_step, executed):
         """Both rooflines of one launch of `eng` that took `ms`."""
         B, R = eng.n_worlds, eng.n_robots
@@ -401,17 +419,37 @@ class Bench:
             executed = eng.step_counted(flags=flags, stream=self.sh)
         except Exception:
             pass
-        total_ms, = self.reduce([total_ms])
+        # the same K steps as one brs_steps call, on a fresh engine stepped through the same
+        # states (a step's cost drifts as the robots move, so both timings see the same steps)
+        eng2 = rb.BatchEngine(scene, device=self.local_rank)
+        call_ms, call_launches = self.time_steps_call(eng2, flags, steps, warmup)
+        eng2.close()
+        total_ms, call_ms = self.reduce([total_ms, call_ms])
         all_tests, = self.reduce([float(tests_per_step)], "sum")
         ms = total_ms / steps
         out = None
         if self.rank == 0:
             avg_launch = sum(launch_ms) / len(launch_ms) if launch_ms else ms
             hbm, fp32 = self.rooflines(eng, avg_launch, tests_per_step, executed)
+            cms = call_ms / steps
+            chbm, cfp32 = self.rooflines(eng, cms, tests_per_step, executed)
+            # one launch = `steps` world-steps per world: per-launch figures scale, rates do not
+            chbm["steps_per_launch"] = cfp32["steps_per_launch"] = steps if call_launches == 1 else 1
+            if call_launches == 1:
+                for d, keys in ((chbm, ("algorithmic_bytes_per_launch", "bytes_written_per_launch")),
+                                (cfp32, ("algorithmic_tests_per_launch", "executed_ray_tests_per_launch",
+                                         "executed_edge_tests_per_launch"))):
+                    for k in keys:
+                        if k in d:
+                            d[k] *= steps
             out = {"config": describe(config, scene), "ms_per_step": ms, "avg_launch_ms": avg_launch,
                    "value": self.world_size * B / (ms * 1e-3), "unit": "world-steps/s",
                    "ray_segment_tests_per_sec": all_tests / (ms * 1e-3), "ray_segment_tests_per_step": all_tests,
-                   "hbm": hbm, "fp32": fp32, "launch": eng.launch_info(), "scene": scene}
+                   "hbm": hbm, "fp32": fp32, "launch": eng.launch_info(), "scene": scene,
+                   "steps_call": {"api": "brs_steps(K): World.steps(K)", "launches": call_launches, "steps": steps,
+                                  "launch_ms": call_ms, "ms_per_step": cms,
+                                  "value": self.world_size * B / (cms * 1e-3),
+                                  "ray_segment_tests_per_sec": all_tests / (cms * 1e-3), "hbm": chbm, "fp32": cfp32}}
         if keep:
             return out, eng, scene
         eng.close()
@@ -610,6 +648,11 @@ def summarize(w):
             "hbm_frac": w["hbm"]["frac"], "fp32_frac": w["fp32"]["frac"],
             "fp32_executed_frac": w["fp32"].get("executed_frac"), "culled_share": w["fp32"].get("culled_share"),
             "executed_tests_per_sec": w["fp32"].get("executed_tests_per_sec"),
+            "steps_call": {"launches": w["steps_call"]["launches"], "ms_per_step": w["steps_call"]["ms_per_step"],
+                           "world_steps_per_sec": w["steps_call"]["value"],
+                           "ray_segment_tests_per_sec": w["steps_call"]["ray_segment_tests_per_sec"],
+                           "hbm_frac": w["steps_call"]["hbm"]["frac"], "fp32_frac": w["steps_call"]["fp32"]["frac"],
+                           "fp32_executed_frac": w["steps_call"]["fp32"].get("executed_frac")},
             "launch": {k: w["launch"][k] for k in ("path", "launches_per_step", "threads", "ctas", "smem_bytes")}}
 
 
@@ -671,7 +714,10 @@ def main():
 
     line = None
     if rank == 0:
-        hbm, fp32 = head["hbm"], head["fp32"]
+        # headline: the K timed steps are ONE call of brs_steps (World.steps(K)); the same K steps
+        # as K calls of brs_step are reported beside it (`per_step_launches`)
+        sc = head["steps_call"]
+        hbm, fp32 = sc["hbm"], sc["fp32"]
         try:
             # context: what a plain streaming-store kernel reaches on this GPU (the path is write-only)
             wc = rb.measure_write_bw(local_rank, 512 << 20, 0, 5)
@@ -695,17 +741,25 @@ def main():
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": dom["peak_source"], "kernel": "brs_step_kernel" if head["launch"]["path"].startswith("fused")
                     else ("brs_solo_kernel" if head["launch"]["path"].startswith("solo") else "brs_wide_kernel"),
-                    "avg_launch_ms": head["avg_launch_ms"], "hbm": hbm, "fp32": fp32}
+                    "avg_launch_ms": sc["launch_ms"] / sc["launches"], "world_steps_per_launch": B * args.steps // sc["launches"],
+                    "hbm": hbm, "fp32": fp32}
         line = {
-            "metric": "world-steps/sec", "value": head["value"], "unit": "world-steps/s", "n_gpus": world_size,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "metric": "world-steps/sec", "value": sc["value"], "unit": "world-steps/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sc["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": head["config"],
             "l2": "no explicit flush: every step streams %.0f MB of fresh observations through a 126 MB L2"
-                  % (hbm["bytes_written_per_launch"] / 1e6),
+                  % (head["hbm"]["bytes_written_per_launch"] / 1e6),
+            "launch_mode": "the %d timed steps are one brs_steps call (upstream World.steps(n)) = %d kernel launch(es): every "
+                           "step writes all of its observations, a tile's steps are ordered by per-tile epochs, the "
+                           "kernel's pipeline runs on across step boundaries" % (args.steps, sc["launches"]),
+            "per_step_launches": {"api": "brs_step x %d" % args.steps, "ms_per_step": head["ms_per_step"],
+                                  "value": head["value"], "avg_launch_ms": head["avg_launch_ms"],
+                                  "hbm_frac": head["hbm"]["frac"], "fp32_frac": head["fp32"]["frac"],
+                                  "ray_segment_tests_per_sec": head["ray_segment_tests_per_sec"]},
             "precision": "FP32 ray search + FP64 winner refinement, FP64 motion/collision",
             "launch": head["launch"],
-            "ray_segment_tests_per_sec": head["ray_segment_tests_per_sec"],
+            "ray_segment_tests_per_sec": sc["ray_segment_tests_per_sec"],
             "ray_segment_tests_per_step": head["ray_segment_tests_per_step"],
             "roofline": roofline,
             "e2e": e2e,
@@ -715,13 +769,18 @@ def main():
             line["gather"] = gather
 
     # ---- the other BASELINE.json configurations, same run (sub-objects of the line) ----
-    if world_size == 1 and not args.no_large_batch and rank == 0 and 4 * line["roofline"]["hbm"]["algorithmic_bytes_per_launch"] < 16e9:
+    if world_size == 1 and not args.no_large_batch and rank == 0 and 4 * head["hbm"]["algorithmic_bytes_per_launch"] < 16e9:
         # supplementary: the same workload at 4x the worlds.  A launch of the named size lasts
         # ~0.1 ms, of which the pipeline fill (first tile of every CTA) and the tail are a fixed
         # ~20 us; the larger batch shows the kernel's steady-state rate.  Not the headline.
         big, _, _ = bench.workload(args.config, 4 * B, args.steps, 3)
-        line["large_batch"] = {"worlds_per_gpu": 4 * B, "ms_per_step": big["ms_per_step"], "value": big["value"],
-                               "hbm_frac": big["hbm"]["frac"], "fp32_frac": big["fp32"]["frac"]}
+        line["large_batch"] = {"worlds_per_gpu": 4 * B, "ms_per_step": big["steps_call"]["ms_per_step"],
+                               "value": big["steps_call"]["value"],
+                               "hbm_frac": big["steps_call"]["hbm"]["frac"], "fp32_frac": big["steps_call"]["fp32"]["frac"],
+                               "per_step_launches": {"ms_per_step": big["ms_per_step"], "value": big["value"],
+                                                     "hbm_frac": big["hbm"]["frac"]},
+                               "note": "hbm_frac is against the measured COPY peak (reads + writes); a write-only stream "
+                                       "can exceed it"}
     if extras:
         ex = {}
         steps_x = max(5, min(args.steps, 20))
@@ -741,10 +800,22 @@ def main():
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
             bench.launches += 1000
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            b0.record(bench.stream)
+            e1.steps(1000, stream=bench.sh)  # World.steps(1000): config 1 exactly as BASELINE.json writes it
+            b1.record(bench.stream)
+            torch.cuda.synchronize()
+            wall_call = time.perf_counter() - t0
+            bench.launches += e1.steps_launches(1000)
             ex["config1"] = {"workload": describe("config1", scene1)["workload"], "worlds": 1, "steps": 1000,
-                             "gpu_seconds_for_1000_steps": a0.elapsed_time(a1) * 1e-3, "host_wall_seconds": wall,
-                             "world_steps_per_sec": 1000.0 / (a0.elapsed_time(a1) * 1e-3),
-                             "note": "one world cannot fill a GPU: this is launch latency; the batched path is config1 x 4096"}
+                             "gpu_seconds_for_1000_steps": b0.elapsed_time(b1) * 1e-3, "host_wall_seconds": wall_call,
+                             "world_steps_per_sec": 1000.0 / (b0.elapsed_time(b1) * 1e-3),
+                             "api": "World.steps(1000) = one brs_steps call, %d launch" % e1.steps_launches(1000),
+                             "per_step_launches": {"gpu_seconds_for_1000_steps": a0.elapsed_time(a1) * 1e-3,
+                                                   "host_wall_seconds": wall,
+                                                   "world_steps_per_sec": 1000.0 / (a0.elapsed_time(a1) * 1e-3)},
+                             "note": "one world cannot fill a GPU: this is latency; the batched path is config1 x 4096"}
             e1.close()
             w, _, _ = bench.workload("config1", 4096, steps_x, 3)
             ex["config1_x4096"] = summarize(w)

@@ -912,3 +912,74 @@ def test_facade_world_picture_and_ground_camera():
     assert tuple(gp[3, 10]) == (0, 0, 255, 255) and tuple(gp[15, 10]) == (0, 128, 0, 255)
     w2 = rb.World.from_json(w.to_json())
     assert isinstance(list(w2)[0][0], rb.GroundCamera) and list(w2)[0][0].view == (40.0, 40.0)
+
+
+@pytest.mark.parametrize("maker,env,plan", [
+    (lambda: rb.scenes.config1(n_worlds=1, seed=1), {}, "fused ("),
+    (lambda: rb.scenes.config1(n_worlds=700, seed=1), {"BRS_SOLO": "0"}, "fused ("),
+    (lambda: rb.scenes.config2(n_worlds=1500, cam_w=64, cam_h=32), {}, "fused ("),
+    (lambda: rb.scenes.config2(n_worlds=96), {"BRS_TW": "2"}, "fused ("),
+    (lambda: rb.scenes.config3(n_worlds=9000), {}, "fused ("),
+    (lambda: rb.scenes.demo_scene(50), {"BRS_BIG": "1"}, "fused ("),
+    (lambda: rb.scenes.config4(n_worlds=9000), {"BRS_SOLO": "1"}, "solo ("),
+    (lambda: rb.scenes.config4(n_worlds=40), {"BRS_SOLO": "1"}, "solo ("),
+    (lambda: rb.scenes.config5(n_worlds=5000, n_segments=100, n_rays=16), {"BRS_SOLO": "1"}, "solo range"),
+    (lambda: rb.scenes.config5(n_worlds=33, n_segments=300, n_rays=64), {"BRS_SOLO": "1"}, "solo range"),
+    # many steps over few tiles: every step of a tile lands on another CTA, the epoch waits are exercised
+    (lambda: rb.scenes.config2(n_worlds=600, cam_w=32, cam_h=16), {"_N": "150"}, "fused ("),
+    (lambda: rb.scenes.config3(n_worlds=3000), {"_N": "60", "BRS_TW": "4"}, "fused ("),
+    (lambda: rb.scenes.demo_scene(700), {"_N": "40"}, "fused ("),
+])
+def test_steps_in_one_launch_equal_single_steps(maker, env, plan):
+    """brs_steps (World.steps(n): one launch, tiles / worlds statically owned, pipelines running
+    on across the step boundaries) leaves every buffer bit-identical to n calls of brs_step --
+    on every plan, for batches smaller and larger than the grid, for move-only steps too."""
+    scene = maker()
+    env = dict(env)
+    n_steps = int(env.pop("_N", "7"))
+
+    def run(how, flags=rb.STEP_ALL, n=n_steps):
+        eng = rb.BatchEngine(scene)
+        assert eng.launch_info()["path"].startswith(plan), eng.launch_info()
+        eng.step()  # (a first step so that velocities have ramped and some robots have stalled)
+        if how == "single":
+            for _ in range(n):
+                eng.step(flags=flags)
+        else:
+            eng.steps(n, flags=flags)
+        eng.synchronize()
+        out = {k: eng.download(k) for k in ("pose", "vel", "stalled", "range", "light", "smell")}
+        if eng.n_camera:
+            out["camera"] = eng.download("camera")
+        eng.close()
+        return out
+
+    for flags in (rb.STEP_ALL, rb.STEP_MOVE):
+        a = _with_env(env, lambda: run("single", flags))
+        b = _with_env(env, lambda: run("steps", flags))
+        c = _with_env(dict(env, BRS_STEPS_ONE_LAUNCH="0"), lambda: run("steps", flags))
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, flags)
+            assert np.array_equal(a[k], c[k]), (k, flags, "fallback")
+    assert np.abs(a["pose"] - scene.pose).max() > 0.5  # they did move
+
+
+def test_facade_steps_is_one_engine_call():
+    """World.steps(n) == n x World.step() on the facade (config 1 as BASELINE.json writes it)."""
+    def make():
+        w = rb.World(200, 150)
+        w.add_wall("blue", 40, 30, 80, 35)
+        r = rb.Robot(100, 75, 0)
+        r.add_device(rb.RangeSensor(position=(8, 0), a=0, max=100, width=0))
+        w.add_robot(r)
+        r.move(0.5, 0.2)
+        return w, r
+
+    w1, r1 = make()
+    w2, r2 = make()
+    for _ in range(100):
+        w1.step()
+    w2.steps(100)
+    assert r1.get_pose() == r2.get_pose() and r1.stalled == r2.stalled
+    assert r1[0].get_distance() == r2[0].get_distance()
+    assert w1.time == w2.time == 10.0
