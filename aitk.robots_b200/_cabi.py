@@ -136,6 +136,7 @@ SYMBOLS = [
     ("brs_step_counted", C.c_int, [_P, C.c_double, C.c_uint, _P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     ("brs_steps", C.c_int, [_P, C.c_double, C.c_uint, C.c_int, _P]),
     ("brs_steps_launches", C.c_int, [_P, C.c_uint, C.c_int, C.POINTER(C.c_int)]),
+    ("brs_steps_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("brs_step_host", C.c_int, [_P, C.c_double, C.c_uint, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("brs_host_alloc", C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
     ("brs_host_free", C.c_int, [_P, _P]),

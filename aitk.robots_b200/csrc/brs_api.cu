@@ -71,6 +71,9 @@ struct brs_engine {
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
   int T = 288, NW = 256, NH = 1, TW = 1, NR = 1, GS = 32, SLG = 1, SLD = 1, SLL = 1, paint_rs = 1, n_tiles = 1, grid = 1, smem = 0;
+  // the same kernel's shape under brs_steps (one launch, many steps): no per-step fill / drain and
+  // no tail to balance, so tiles can be larger (config 2 at 4,096 worlds: TW 1 -> 4, 5.9 -> 6.9 TB/s)
+  int mTW = 1, mSLG = 1, mSLD = 1, mSLL = 1, m_paint_rs = 1, m_tiles = 1, m_grid = 1, m_smem = 0, m_fused_table = 0;
   int gtasks = 0, dtasks = 0;
   bool big = false, direct_on_helper = false;
   int fused_table = 0;
@@ -111,7 +114,7 @@ struct brs_engine {
   // kernel parameters cached per step-flags value (everything but dt and the rebindable outputs is fixed at create)
   KParams kp_cache;
   unsigned kp_flags = 0xffffffffu;
-  bool kp_wide = false;
+  bool kp_wide = false, kp_msteps = false;
 };
 
 static int pow2floor(int x) {
@@ -574,17 +577,27 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   const int per_slot = work < 20000.0 ? 2 : 6;
   int tw_max = std::min(64, std::max(1, cfg->n_worlds / (slots * per_slot)));
   while (tw_max > 1 && smem_for(tw_max) > budget) --tw_max;
-  int tw = tw_max;
-  {
+  auto pick_tw = [&](int tmax) {
+    int pick = tmax;
     double best = -1;
-    for (int t = tw_max; t >= 1; --t) {
+    for (int t = tmax; t >= 1; --t) {
       const int n = t * tasks, passes = (n + e->NW - 1) / e->NW;
       const double eff = (double)n / ((double)passes * e->NW);
-      if (eff > best + 0.05) { best = eff; tw = t; }
+      if (eff > best + 0.05) { best = eff; pick = t; }
     }
-  }
+    return pick;
+  };
+  int tw = pick_tw(tw_max);
   tw = env_int("BRS_TW", tw);
   tw = std::max(1, std::min(tw, cfg->n_worlds));
+  // brs_steps: ~1.5 tiles per resident CTA are enough (the two teams need two tiles in flight)
+  int mtw_max = std::min(64, std::max(1, (int)(cfg->n_worlds / (slots * 1.5))));
+  while (mtw_max > 1 && smem_for(mtw_max) > budget) --mtw_max;
+  int mtw = std::max(tw, pick_tw(mtw_max));
+  if (getenv("BRS_TW")) mtw = tw;
+  mtw = env_int("BRS_STEPS_TW", mtw);
+  mtw = std::max(1, std::min(mtw, cfg->n_worlds));
+  if ((size_t)smem_for(mtw) > prop.sharedMemPerBlockOptin) mtw = tw;
   e->TW = tw;
   e->smem = smem_for(tw);
   if ((size_t)e->smem > prop.sharedMemPerBlockOptin) {
@@ -594,23 +607,33 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->n_tiles = (cfg->n_worlds + tw - 1) / tw;
   e->T = e->NW + 32 * e->NH;
   e->GS = std::min(32 * e->NH, std::max(8, pow2ceil(cfg->seg_cap)));  // helper threads per (world, robot)
-  e->SLG = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * tw), 1))) : 1;
   const int dteam = e->direct_on_helper ? 32 * e->NH : e->NW;  // threads that run the direct path
-  e->SLD = e->n_dr ? std::min(32, pow2floor(std::max(dteam / (e->n_dr * tw), 1))) : 1;
-  e->SLL = cfg->n_light ? std::min(32, pow2floor(std::max(dteam / (cfg->n_light * tw), 1))) : 1;
-  {
+  auto lanes_for = [&](int t, int& slg, int& sld, int& sll, int& prs) {
+    slg = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * t), 1))) : 1;
+    sld = e->n_dr ? std::min(32, pow2floor(std::max(dteam / (e->n_dr * t), 1))) : 1;
+    sll = cfg->n_light ? std::min(32, pow2floor(std::max(dteam / (cfg->n_light * t), 1))) : 1;
     const int Q = std::max(e->cam_w / 4, 1);
     const int slots = std::max(e->NW / std::min(Q, e->NW), 1);
-    const int nislot = std::max(1, std::min(tw * std::max(cfg->n_camera, 1), slots));
-    e->paint_rs = std::max(1, slots / nislot);
-  }
+    const int nislot = std::max(1, std::min(t * std::max(cfg->n_camera, 1), slots));
+    prs = std::max(1, slots / nislot);
+  };
+  lanes_for(tw, e->SLG, e->SLD, e->SLL, e->paint_rs);
+  e->mTW = mtw;
+  e->m_smem = smem_for(mtw);
+  e->m_tiles = (cfg->n_worlds + mtw - 1) / mtw;
+  lanes_for(mtw, e->mSLG, e->mSLD, e->mSLL, e->m_paint_rs);
   if (e->NR == 4) e->NR = 2;  // (4 columns per thread measured slower than 2)
   const void* kfn = e->big ? (e->NR == 2 ? (const void*)brs_step_kernel<2, true> : (const void*)brs_step_kernel<1, true>)
                            : (e->NR == 2 ? (const void*)brs_step_kernel<2, false> : (const void*)brs_step_kernel<1, false>);
   e->kfn = kfn;
-  cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem);
-  int nb = 0;
+  cudaError_t ce = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(e->smem, e->m_smem));
+  int nb = 0, mnb = 0;
   if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, e->T, e->smem);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mnb, kfn, e->T, e->m_smem);
+  if (ce == cudaSuccess && mnb < 1) {  // (cannot happen within the budget; fall back to the single-step shape)
+    e->mTW = e->TW; e->m_smem = e->smem; e->m_tiles = e->n_tiles; mnb = nb;
+    e->mSLG = e->SLG; e->mSLD = e->SLD; e->mSLL = e->SLL; e->m_paint_rs = e->paint_rs;
+  }
   if (ce != cudaSuccess || nb < 1) {
     brs_destroy(e);
     return fail(BRS_ERR_CUDA, std::string("brs_create: kernel does not fit: ") + cudaGetErrorString(ce));
@@ -619,6 +642,9 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   e->f_ctas_per_sm = nb;
   e->grid = std::max(1, std::min(e->n_tiles, nb * e->sm_count));
   e->fused_table = env_int("BRS_FUSED_TABLE", e->TW * e->n_group >= e->NW / 32 ? 1 : 0);
+  mnb = std::min(mnb, env_int("BRS_MAX_CTAS_PER_SM", 32));
+  e->m_grid = std::max(1, std::min(e->m_tiles, mnb * e->sm_count));
+  e->m_fused_table = env_int("BRS_FUSED_TABLE", e->mTW * e->n_group >= e->NW / 32 ? 1 : 0);
 
   // ---- the wide path: launch geometry ------------------------------------------
   // One team (CTA) per tile, no helper warps.  A one-warp team wherever a tile of worlds fits
@@ -1011,12 +1037,13 @@ extern "C" int brs_download(brs_engine* e, int which, void* host, int first_worl
 
 // Kernel parameters of one step: everything but flags, dt and the (rebindable) output
 // pointers is fixed at brs_create.
-static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide);
-static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide) {
-  if (e->kp_flags != flags || e->kp_wide != wide) {
-    fill_params_uncached(e, e->kp_cache, time_step, flags, wide);
+static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide, bool msteps);
+static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide, bool msteps = false) {
+  if (e->kp_flags != flags || e->kp_wide != wide || e->kp_msteps != msteps) {
+    fill_params_uncached(e, e->kp_cache, time_step, flags, wide, msteps);
     e->kp_flags = flags;
     e->kp_wide = wide;
+    e->kp_msteps = msteps;
   }
   p = e->kp_cache;
   p.dt = time_step;
@@ -1031,7 +1058,7 @@ static void fill_params(brs_engine* e, KParams& p, double time_step, unsigned fl
   p.noise.step_lo = (uint32_t)(e->noise_step & 0xffffffffull);
   p.noise.step_hi = (uint32_t)(e->noise_step >> 32);
 }
-static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide) {
+static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, unsigned flags, bool wide, bool msteps) {
   const brs_config& c = e->cfg;
   memset(&p, 0, sizeof(p));
   p.n_worlds = c.n_worlds; p.n_robots = c.n_robots; p.seg_cap = c.seg_cap; p.n_bulbs = c.n_bulbs;
@@ -1051,6 +1078,10 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
     p.TW = e->TW; p.n_tiles = e->n_tiles; p.SLG = e->SLG; p.SLD = e->SLD; p.SLL = e->SLL; p.paint_rs = e->paint_rs;
     p.direct_on_helper = e->direct_on_helper ? 1 : 0;
     p.fused_table = e->fused_table;
+    if (msteps) {
+      p.TW = e->mTW; p.n_tiles = e->m_tiles; p.SLG = e->mSLG; p.SLD = e->mSLD; p.SLL = e->mSLL; p.paint_rs = e->m_paint_rs;
+      p.fused_table = e->m_fused_table;
+    }
     p.NW = e->NW; p.NH = e->NH;
     p.cq_max = BRS_CQ_MAX;
     p.prepped = e->prep_fused ? 1 : 0;
@@ -1100,7 +1131,7 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
     p.m_rays = e->d_multi_rays; p.m_nrays = e->multi_nrays; p.m_bw = e->multi_bw;
   }
   if (e->use_rlist && !e->solo) {
-    const int tw = wide ? e->wTW : e->TW, R = c.n_robots, nvis = c.seg_cap + 4 * R;
+    const int tw = wide ? e->wTW : (msteps ? e->mTW : e->TW), R = c.n_robots, nvis = c.seg_cap + 4 * R;
     const int base = wide ? make_wide_layout(tw, c.seg_cap, R, e->n_group, c.n_camera, e->cam_w, e->cam_h, !e->w_big, e->wNT > 32).total
                           : make_layout(tw, c.seg_cap, R, e->n_group, c.n_camera, e->cam_w, e->cam_h, !e->big).total;
     p.use_rlist = 1;
@@ -1117,11 +1148,12 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
 // dimension, so a sub-range is the same kernel on shifted base pointers.
 static int launch_range(brs_engine* e, int first, int n, double time_step, unsigned flags, void* stream, int n_steps = 1) {
   KParams p;
-  fill_params(e, p, time_step, flags, e->wide);
+  const bool msteps = n_steps > 1 && !e->solo && !e->wide;  // the fused kernel's brs_steps shape
+  fill_params(e, p, time_step, flags, e->wide, msteps);
   p.n_steps = n_steps;
   p.epoch0 = e->epoch0;
   const brs_config& c = e->cfg;
-  int grid = e->solo ? e->s_grid : e->wide ? e->w_grid : e->grid;
+  int grid = e->solo ? e->s_grid : e->wide ? e->w_grid : (msteps ? e->m_grid : e->grid);
   if (first != 0 || n != c.n_worlds) {
     const size_t R = c.n_robots, f = (size_t)first;
     p.seg += f * 5 * c.seg_cap; p.seg_count += f; p.world_size += 2 * f;
@@ -1144,7 +1176,7 @@ static int launch_range(brs_engine* e, int first, int n, double time_step, unsig
   if (e->solo) {
     CK(cudaLaunchKernel(e->s_kfn, dim3(grid), dim3(e->sNT), args, (size_t)e->s_smem, (cudaStream_t)stream));
   } else if (!e->wide && !e->prep_fused) {
-    CK(cudaLaunchKernel(e->kfn, dim3(grid), dim3(e->T), args, (size_t)e->smem, (cudaStream_t)stream));
+    CK(cudaLaunchKernel(e->kfn, dim3(grid), dim3(e->T), args, (size_t)(msteps ? e->m_smem : e->smem), (cudaStream_t)stream));
   } else {
     // prep (thread per robot half), then the step kernel under programmatic dependent launch:
     // its prologue and first wall copies overlap the prep kernel, griddepcontrol.wait orders the rest
@@ -1186,7 +1218,7 @@ static bool steps_one_launch(const brs_engine* e, unsigned flags, int n_steps) {
 }
 // (the fused kernel counts (step, tile) items in 32 bits: very long runs go in pieces)
 static int steps_piece(const brs_engine* e, int n_steps) {
-  const int tiles = e->solo ? 1 : std::max(e->n_tiles, 1);
+  const int tiles = e->solo ? 1 : std::max(e->m_tiles, 1);
   return std::max(2, (int)std::min<long long>(n_steps, 0x3fffffffll / tiles));
 }
 extern "C" int brs_steps_launches(brs_engine* e, unsigned flags, int n_steps, int* launches) {
@@ -1197,6 +1229,16 @@ extern "C" int brs_steps_launches(brs_engine* e, unsigned flags, int n_steps, in
   else *launches = ((flags & BRS_STEP_MOVE) ? n_steps : 1) * per;
   return BRS_OK;
 }
+// the launch shape brs_steps uses when it runs as one launch (the fused kernel picks larger tiles for it)
+extern "C" int brs_steps_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* ctas, int* smem_bytes) {
+  if (!e) return fail(BRS_ERR_INVALID, "brs_steps_info: null engine");
+  const bool fused = !e->solo && !e->wide;
+  if (worlds_per_tile) *worlds_per_tile = e->solo ? 1 : fused ? e->mTW : e->wTW;
+  if (n_tiles) *n_tiles = e->solo ? e->cfg.n_worlds : fused ? e->m_tiles : e->w_tiles;
+  if (ctas) *ctas = e->solo ? e->s_grid : fused ? e->m_grid : e->w_grid;
+  if (smem_bytes) *smem_bytes = e->solo ? e->s_smem : fused ? e->m_smem : e->w_smem;
+  return BRS_OK;
+}
 extern "C" int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_steps, void* stream) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_steps: null engine");
   if (n_steps < 0) return fail(BRS_ERR_INVALID, "brs_steps: n_steps < 0");
@@ -1204,7 +1246,7 @@ extern "C" int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_
   CK(cudaSetDevice(e->cfg.device));
   const bool one_launch = steps_one_launch(e, flags, n_steps);
   if (one_launch) {
-    const int tiles = e->solo ? 1 : std::max(e->n_tiles, 1);
+    const int tiles = e->solo ? 1 : std::max(e->m_tiles, 1);
     const int piece = steps_piece(e, n_steps);
     for (int done = 0; done < n_steps;) {
       const int n = std::min(piece, n_steps - done);
@@ -1497,11 +1539,17 @@ extern "C" int brs_measure_write_bw(int device, size_t bytes, int mode, int reps
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a));
   CK(cudaEventCreate(&b));
-  brs_fill_kernel<<<blocks, 256>>>(d, n16, mode);  // warm-up
+  // mode 0 / 1: grid-stride 16-byte stores (st.cs / default); 2: the driver's cudaMemsetAsync;
+  // 3: CTA-contiguous 128 KB chunks of st.cs (the shape of PAINT)
+  auto fill = [&]() {
+    if (mode == 2) cudaMemsetAsync(d, 0x5a, n16 * 16, 0);
+    else brs_fill_kernel<<<mode == 3 ? prop.multiProcessorCount * 4 : blocks, 256>>>(d, n16, mode);
+  };
+  fill();  // warm-up
   double best = 0;
   for (int r = 0; r < reps; ++r) {
     CK(cudaEventRecord(a));
-    brs_fill_kernel<<<blocks, 256>>>(d, n16, mode);
+    fill();
     CK(cudaEventRecord(b));
     CK(cudaEventSynchronize(b));
     float ms = 0;

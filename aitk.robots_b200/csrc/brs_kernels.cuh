@@ -1909,6 +1909,16 @@ __global__ void __launch_bounds__(1024) brs_ffma_kernel(float* out, int iters, f
 // ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) brs_fill_kernel(uint4* out, size_t n16, int mode) {
   const uint4 v = make_uint4(threadIdx.x, blockIdx.x, 0xff00ff00u, 0xffffffffu);
+  if (mode == 3) {
+    // CTA-contiguous: a CTA streams whole 128 KB chunks (one config-2 picture), like PAINT does
+    const size_t per = 8192, nchunk = n16 / per;
+    for (size_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
+      uint4* o = out + c * per;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < (int)per; i += 256) __stcs(o + i, v);
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
     if (mode == 0)
       __stcs(out + i, v);

@@ -275,6 +275,12 @@ class BatchEngine:
         cabi.check(self._lib.brs_steps_launches(self._h, int(flags), int(n), C.byref(k)))
         return int(k.value)
 
+    def steps_info(self):
+        """Launch shape of a one-launch steps(): worlds per tile, tiles, CTAs, shared memory."""
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        cabi.check(self._lib.brs_steps_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"worlds_per_tile": a.value, "tiles": b.value, "ctas": c.value, "smem_bytes": d.value}
+
     def step_host(self, time_step=None, flags=cabi.STEP_ALL, target_vel=0, pose=0, stalled=0, range_=0, camera=0,
                   light=0, smell=0, stream=0):
         """The same step with HOST (pinned) buffers given as raw addresses (0 = skip)."""

@@ -28,10 +28,12 @@ class VecEnv:
     step) minus ``stall_penalty`` per stalled robot, and end an episode after
     ``max_steps`` steps.  Finished worlds are reset in place (pose, velocities,
     step counter) before the next step, so ``step`` always returns live worlds.
+    ``frame_skip=k`` repeats every action for k World.steps (k-1 move-only steps in one
+    launch, then one full step); rewards and observations are those after the k-th.
     """
 
     def __init__(self, scene, device=0, max_steps=1000, stall_penalty=1.0, reward_fn=None, done_fn=None,
-                 camera=True):
+                 camera=True, frame_skip=1):
         import torch
 
         self.torch = torch
@@ -40,6 +42,9 @@ class VecEnv:
         self.n_worlds, self.n_robots = e.n_worlds, e.n_robots
         self.max_steps, self.stall_penalty = int(max_steps), float(stall_penalty)
         self.reward_fn, self.done_fn = reward_fn, done_fn
+        # action repeat: one env step = frame_skip World.steps with the same action; only the
+        # last one senses (the others are move-only steps, all in one brs_steps launch)
+        self.frame_skip = max(1, int(frame_skip))
         self.flags = cabi.STEP_MOVE | cabi.STEP_SENSE | (cabi.STEP_CAMERA if (camera and e.n_camera) else 0)
         dev = torch.device("cuda", e.device)
         # zero-copy views of engine memory
@@ -90,8 +95,10 @@ class VecEnv:
         self.target_vel[..., 0] = a[..., 0] * self._scale[:, 0]
         self.target_vel[..., 2] = a[..., 1] * self._scale[:, 1]
         self._prev_xy.copy_(self.pose[..., :2])
+        if self.frame_skip > 1:
+            self.engine.steps(self.frame_skip - 1, flags=cabi.STEP_MOVE, stream=self._stream())
         self.engine.step(flags=self.flags, stream=self._stream())  # the step launch
-        self.steps += 1
+        self.steps += self.frame_skip
         if self.reward_fn is not None:
             reward = self.reward_fn(self)
         else:

@@ -447,6 +447,7 @@ class Bench:
                    "ray_segment_tests_per_sec": all_tests / (ms * 1e-3), "ray_segment_tests_per_step": all_tests,
                    "hbm": hbm, "fp32": fp32, "launch": eng.launch_info(), "scene": scene,
                    "steps_call": {"api": "brs_steps(K): World.steps(K)", "launches": call_launches, "steps": steps,
+                                  "shape": eng.steps_info(),
                                   "launch_ms": call_ms, "ms_per_step": cms,
                                   "value": self.world_size * B / (cms * 1e-3),
                                   "ray_segment_tests_per_sec": all_tests / (cms * 1e-3), "hbm": chbm, "fp32": cfp32}}
@@ -720,16 +721,25 @@ def main():
         hbm, fp32 = sc["hbm"], sc["fp32"]
         try:
             # context: what a plain streaming-store kernel reaches on this GPU (the path is write-only)
-            wc = rb.measure_write_bw(local_rank, 512 << 20, 0, 5)
+            modes = {"grid-stride st.cs": 0, "cudaMemsetAsync": 2, "CTA-contiguous 128 KB chunks of st.cs": 3}
+            got = {k: rb.measure_write_bw(local_rank, 2048 << 20, m, 5) for k, m in modes.items()}
+            wc = max(got.values())
             hbm["write_only_ceiling_gbs"] = wc
+            hbm["write_only_ceiling_by_pattern"] = got
             hbm["frac_of_write_only_ceiling"] = hbm["achieved"] / wc
+            hbm["note"] = ("peak is MEASURED_PEAKS.json's COPY bandwidth (read + write bytes of b.copy_(a)); this path only "
+                           "writes, and a write-only stream can exceed a copy's byte rate -- write_only_ceiling_gbs is the "
+                           "best plain store kernel / memset on this GPU, measured in this run")
         except Exception:
             pass
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "r2", "traffic_%s.json" % args.config)
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+            # (per launch, like `achieved`: the capture's per-step DRAM bytes x the steps of this launch)
+            per_step = tj.get("dram_bytes_per_step", tj.get("dram_bytes_per_launch"))
+            traffic = per_step * (args.steps // sc["launches"]) if per_step is not None else None
+            traffic_src = tj.get("source")
         pipes = pipe_utilisation(args.config)
         if pipes:
             fp32["ncu_pipes"] = pipes
@@ -753,6 +763,7 @@ def main():
             "launch_mode": "the %d timed steps are one brs_steps call (upstream World.steps(n)) = %d kernel launch(es): every "
                            "step writes all of its observations, a tile's steps are ordered by per-tile epochs, the "
                            "kernel's pipeline runs on across step boundaries" % (args.steps, sc["launches"]),
+            "steps_launch_shape": sc["shape"],
             "per_step_launches": {"api": "brs_step x %d" % args.steps, "ms_per_step": head["ms_per_step"],
                                   "value": head["value"], "avg_launch_ms": head["avg_launch_ms"],
                                   "hbm_frac": head["hbm"]["frac"], "fp32_frac": head["fp32"]["frac"],

@@ -176,6 +176,9 @@ int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
 int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_steps, void* stream);
 /* How many kernel launches brs_steps(flags, n_steps) issues on this engine as configured now. */
 int brs_steps_launches(brs_engine* e, unsigned flags, int n_steps, int* launches);
+/* The launch shape of a one-launch brs_steps: worlds per tile (the fused kernel takes larger tiles
+ * than for a single step -- no per-step tail to balance), tiles, CTAs, dynamic shared memory. */
+int brs_steps_info(brs_engine* e, int* worlds_per_tile, int* n_tiles, int* ctas, int* smem_bytes);
 
 /* The fused picture gather.  With n_peers > 0 the kernel that paints BRS_BUF_CAMERA also stores
  * every picture at peer_ptrs[k] -- memory of another GPU mapped into this process (CUDA IPC,
@@ -285,7 +288,8 @@ int brs_path_info(brs_engine* e, int* wide, int* launches_per_step);
 int brs_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz);
 
 /* HBM write-bandwidth microbenchmark on `device`: streams `bytes` of 16-byte stores
- * (mode 0: st.global.cs as the PAINT phase uses, 1: default cache policy), best of
+ * (mode 0: grid-stride st.global.cs, 1: grid-stride default cache policy, 2: cudaMemsetAsync,
+ * 3: CTA-contiguous 128 KB chunks of st.global.cs -- the shape of the PAINT phase), best of
  * `reps` launches timed with CUDA events, in GB/s.  Roofline context only. */
 int brs_measure_write_bw(int device, size_t bytes, int mode, int reps, double* gbs);
 

@@ -983,3 +983,26 @@ def test_facade_steps_is_one_engine_call():
     assert r1.get_pose() == r2.get_pose() and r1.stalled == r2.stalled
     assert r1[0].get_distance() == r2[0].get_distance()
     assert w1.time == w2.time == 10.0
+
+
+def test_vec_env_frame_skip_equals_repeated_actions():
+    """VecEnv(frame_skip=k): one env step == k env steps of a plain VecEnv with the same action."""
+    import torch
+
+    scene = rb.scenes.demo_scene(40)
+    a = rb.VecEnv(scene, max_steps=10**6, frame_skip=4)
+    b = rb.VecEnv(scene, max_steps=10**6)
+    a.reset()
+    b.reset()
+    g = torch.Generator().manual_seed(5)
+    for _ in range(6):
+        act = torch.rand((scene.n_worlds, scene.n_robots, 2), generator=g) * 2 - 1
+        oa, _, _, ia = a.step(act)
+        for _ in range(4):
+            ob, _, _, ib = b.step(act)
+        assert torch.equal(a.pose, b.pose) and torch.equal(ia["stalled"], ib["stalled"])
+        for k in oa:
+            assert torch.equal(oa[k], ob[k]), k
+    assert int(a.steps[0]) == 24
+    a.close()
+    b.close()

@@ -3,7 +3,8 @@
 bench lines, per-capture ncu key metrics + instruction share per code region, hot lines, and
 the pipe-utilisation / DRAM-traffic numbers bench.py quotes (pipes.json, traffic_<config>.json).
 
-usage: tools/collect_profiles.py <tag> <prefix> [capture=config ...]   e.g.  r2g a c4_solo=config4
+usage: tools/collect_profiles.py <tag> <prefix> [capture=config[:steps_per_launch] ...]   e.g.  r2g a c4_solo=config4
+       (a capture of a brs_steps launch names how many steps the launch ran: config2_steps=config2:10)
 """
 import csv
 import glob
@@ -46,6 +47,9 @@ for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
     m = dict(zip(rows[0], rows[2]))
     num = lambda k: float(m[k].replace(",", "")) if k in m and m[k] not in ("", "n/a") else None  # noqa: E731
     cfg = capmap.get(name)
+    spl = 1
+    if cfg and ":" in cfg:
+        cfg, spl = cfg.split(":")[0], int(cfg.split(":")[1])
     if cfg:
         pipes[cfg] = {
             "kernel": m.get("Kernel Name"), "source": "profiles/r2/%s_ncu_summary_%s.txt" % (prefix, name),
@@ -58,14 +62,14 @@ for rep in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
             "shared_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
             "shared_bank_conflicts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
             "warp_instructions": num("smsp__inst_executed.sum"),
-            "gpu_time_us_under_ncu": num("gpu__time_duration.sum"),
+            "gpu_time_us_under_ncu": num("gpu__time_duration.sum"), "steps_per_launch": spl,
         }
         rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
         if rd is not None and wr is not None:
             unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             u = dict(zip(rows[0], rows[1]))
             tot = rd * unit.get(u.get("dram__bytes_read.sum"), 1.0) + wr * unit.get(u.get("dram__bytes_write.sum"), 1.0)
-            json.dump({"dram_bytes_per_launch": tot, "source": "ncu --set full, %s_ncu_summary_%s.txt (gpurun call %s, commit %s)"
+            json.dump({"dram_bytes_per_launch": tot, "steps_per_launch": spl, "dram_bytes_per_step": tot / spl, "source": "ncu --set full, %s_ncu_summary_%s.txt (gpurun call %s, commit %s)"
                        % (prefix, name, tag, head)}, open(os.path.join(dst, "traffic_%s.json" % cfg), "w"), indent=1)
 json.dump(pipes, open(pipes_path, "w"), indent=1)
 for f in glob.glob(os.path.join(src, "launches_*.csv")):
