@@ -9,6 +9,7 @@
 #include "brs_wide.cuh"
 #include "brs_solo.cuh"
 #include "brs_multi.cuh"
+#include "brs_mini.cuh"
 
 #include <sched.h>
 
@@ -95,6 +96,9 @@ struct brs_engine {
   GroupDev h_scan_group;
   SoloRay* d_scan_rays = nullptr;
   int scan_nrays = 0, scan_SL = 1, scan_NRL = 1;
+  // the mini range path (brs_mini_kernel): a team of mini_G lanes per world, small range-sensor worlds
+  bool mini = false;
+  int mini_G = 4, mini_NRAY = 1;
   // the solo multi path (brs_multi_kernel): several robots (or several mounts), no camera
   bool use_rlist = false;  // fused / wide: per-robot lists of reachable segments for the direct-path range sensors
   bool multi = false;
@@ -833,6 +837,49 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
       if (e->scan) { e->solo = true; e->wide = false; e->prep_fused = false; }  // (solo = "a warp-per-world plan is active")
     }
   }
+  // ---- the mini range path: launch geometry -------------------------------------
+  // (same shapes as the solo range path, at most 16 rays; wins where a world is too little work
+  // for a whole warp -- measured over the config 5 sweep, profiles/r2)
+  if (scan_shape && e->scan_nrays <= 16 && e->scan_nrays >= 1) {
+    const int K = e->scan_nrays;
+    const int nray = pow2ceil(K);
+    // lanes per world: enough to cover a world's walls a few at a time and to fill the GPU's
+    // thread slots with the batch
+    // (measured over the low-ray cells of the config 5 sweep, profiles/r2/sweep_config5_mini.txt:
+    // 4 lanes up to ~100 walls, 16 beyond)
+    int G = cfg->seg_cap <= 128 ? 4 : 16;
+    G = std::max(2, std::min(16, pow2floor(env_int("BRS_MINI_G", G))));
+    const void* mk = nullptr;
+#define BRS_MK1(GG, NN) (const void*)brs_mini_kernel<GG, NN, 128, (NN >= 16 ? 4 : NN >= 8 ? 6 : 8)>
+#define BRS_MK(GG) (nray == 1 ? BRS_MK1(GG, 1) : nray == 2 ? BRS_MK1(GG, 2) : nray == 4 ? BRS_MK1(GG, 4) : nray == 8 ? BRS_MK1(GG, 8) : BRS_MK1(GG, 16))
+    mk = G == 2 ? BRS_MK(2) : G == 4 ? BRS_MK(4) : G == 8 ? BRS_MK(8) : BRS_MK(16);
+#undef BRS_MK
+#undef BRS_MK1
+    const MiniLayout ML = make_mini_layout(cfg->n_range, K, 128 / G);
+    int mnb = 0;
+    ce = cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, ML.total);
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mnb, mk, 128, ML.total);
+    const bool ok = ce == cudaSuccess && mnb >= 1 && (size_t)ML.total <= prop.sharedMemPerBlockOptin;
+    if (!ok) cudaGetLastError();
+    // auto: worlds whose (walls x rays) work is below what keeps a warp busy, in batches that
+    // fill the machine with teams (measured: see DESIGN.md, the config 5 sweep)
+    const bool small_world = (long long)cfg->seg_cap * (5 + K) < (long long)env_int("BRS_MINI_MAX_WORK", 3000);
+    // (any batch size: one world x 1000 steps -- config 1 as written -- is 2.8 us per step here
+    // against 3.5 on the fused kernel; an explicit BRS_SOLO keeps its meaning: fused or warp per world)
+    const bool auto_mini = ok && small_world && !getenv("BRS_SOLO");
+    if (ok && env_int("BRS_MINI", auto_mini ? 1 : 0) != 0 && env_int("BRS_SOLO", 1) != 0) {
+      e->mini = true; e->mini_G = G; e->mini_NRAY = nray;
+      e->scan = true; e->solo = true; e->wide = false; e->prep_fused = false;
+      e->sNT = 128;
+      e->s_smem = ML.total;
+      e->s_kfn = mk;
+      mnb = std::min(mnb, env_int("BRS_SOLO_MAX_CTAS", 32));
+      e->s_ctas_per_sm = mnb;
+      e->s_warps_per_sm = mnb * 4;
+      const int wpc = 128 / G;
+      e->s_grid = std::max(1, std::min((cfg->n_worlds + wpc - 1) / wpc, mnb * e->sm_count));
+    }
+  }
   // ---- the solo multi path: launch geometry -------------------------------------
   if (multi_shape && !e->solo) {
     const int bw = std::max(1, 16 / pow2ceil(R));
@@ -1166,7 +1213,7 @@ static int launch_range(brs_engine* e, int first, int n, double time_step, unsig
     p.noise.world0 += (uint32_t)first;
     p.n_tiles = (n + p.TW - 1) / p.TW;
     if (e->solo) {
-      const int wpc = e->sNT / 32;
+      const int wpc = e->mini ? e->sNT / e->mini_G : e->sNT / 32;
       grid = std::max(1, std::min((n + wpc - 1) / wpc, e->s_ctas_per_sm * e->sm_count));
     } else {
       grid = std::max(1, std::min(p.n_tiles, (e->wide ? e->w_ctas_per_sm : e->f_ctas_per_sm) * e->sm_count));
@@ -1474,7 +1521,7 @@ extern "C" int brs_launch_info(brs_engine* e, int* threads, int* ctas, int* smem
 
 extern "C" int brs_path_info(brs_engine* e, int* wide, int* launches_per_step) {
   if (!e) return fail(BRS_ERR_INVALID, "brs_path_info: null engine");
-  if (wide) *wide = e->multi ? 5 : e->scan ? 4 : e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
+  if (wide) *wide = e->mini ? 6 : e->multi ? 5 : e->scan ? 4 : e->solo ? 3 : e->wide ? 1 : (e->prep_fused ? 2 : 0);
   if (launches_per_step) *launches_per_step = (!e->solo && (e->wide || e->prep_fused)) ? 2 : 1;
   return BRS_OK;
 }

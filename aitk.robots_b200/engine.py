@@ -328,7 +328,8 @@ class BatchEngine:
         return {"path": ("fused (one kernel)", "wide (prep + step kernel, PDL)", "fused fed by the prep kernel (PDL)",
                          "solo (one warp per world, one kernel)",
                          "solo range (one warp per world, walls streamed, one kernel)",
-                         "solo multi (one warp per world, several robots, one kernel)")[wide.value],
+                         "solo multi (one warp per world, several robots, one kernel)",
+                         "mini range (a team of 2..16 lanes per world, one kernel)")[wide.value],
                 "launches_per_step": nl.value, "threads": t.value, "ctas": c.value, "smem_bytes": s.value,
                 "sm_count": m.value, "worlds_per_tile": tw.value, "tiles": nt.value, "workers": nw.value,
                 "cols_per_thread": nr.value, "ray_groups": ng.value}

@@ -750,7 +750,9 @@ def main():
         roofline = {"bound": "hbm" if dom is hbm else "fp32", "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": dom["peak_source"], "kernel": "brs_step_kernel" if head["launch"]["path"].startswith("fused")
-                    else ("brs_solo_kernel" if head["launch"]["path"].startswith("solo") else "brs_wide_kernel"),
+                    else ("brs_mini_kernel" if head["launch"]["path"].startswith("mini") else
+                          "brs_scan_kernel" if head["launch"]["path"].startswith("solo range") else
+                          "brs_solo_kernel" if head["launch"]["path"].startswith("solo") else "brs_wide_kernel"),
                     "avg_launch_ms": sc["launch_ms"] / sc["launches"], "world_steps_per_launch": B * args.steps // sc["launches"],
                     "hbm": hbm, "fp32": fp32}
         line = {

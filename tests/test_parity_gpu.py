@@ -915,7 +915,10 @@ def test_facade_world_picture_and_ground_camera():
 
 
 @pytest.mark.parametrize("maker,env,plan", [
-    (lambda: rb.scenes.config1(n_worlds=1, seed=1), {}, "fused ("),
+    (lambda: rb.scenes.config1(n_worlds=1, seed=1), {"BRS_MINI": "0"}, "fused ("),
+    (lambda: rb.scenes.config1(n_worlds=1, seed=1), {}, "mini range"),
+    (lambda: rb.scenes.config5(n_worlds=5000, n_segments=30, n_rays=4), {}, "mini range"),
+    (lambda: rb.scenes.config5(n_worlds=70, n_segments=200, n_rays=2), {"_N": "40"}, "mini range"),
     (lambda: rb.scenes.config1(n_worlds=700, seed=1), {"BRS_SOLO": "0"}, "fused ("),
     (lambda: rb.scenes.config2(n_worlds=1500, cam_w=64, cam_h=32), {}, "fused ("),
     (lambda: rb.scenes.config2(n_worlds=96), {"BRS_TW": "2"}, "fused ("),
@@ -1006,3 +1009,86 @@ def test_vec_env_frame_skip_equals_repeated_actions():
     assert int(a.steps[0]) == 24
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("S,rays", [(12, 1), (12, 7), (10, 16), (30, 4), (100, 16), (100, 3), (300, 1), (2000, 2)])
+def test_mini_path_bit_identical_and_matches_the_oracle(S, rays):
+    """The mini range path (a team of 2..16 lanes per world, everything in registers;
+    brs_mini_kernel) against the fused kernel searching the same shared-origin table
+    (BRS_GROUP_MIN=1) and the solo range path, bit for bit, with every team size, and against the
+    oracle; ragged / empty worlds, robots driven into walls, batches that do not fill a warp."""
+    B = 37 if S < 1000 else 9
+    scene = rb.scenes.config5(n_worlds=B, n_segments=S, n_rays=rays)
+    scene.seg_count[1] = 0
+    scene.seg_count[2] = min(S, 5)
+    scene.target_vel[:, :, 0] = np.linspace(-2.0, 2.0, B)[:, None]
+
+    def mini():
+        eng = rb.BatchEngine(scene)
+        assert eng.launch_info()["path"].startswith("mini range"), eng.launch_info()
+        eng.close()
+        return parity.run_engine(scene, 6)
+
+    a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0", "BRS_GROUP_MIN": "1"}, lambda: parity.run_engine(scene, 6))
+    s = _with_env({"BRS_SOLO": "1", "BRS_MINI": "0"}, lambda: parity.run_engine(scene, 6))
+    for env in ({"BRS_MINI": "1"}, {"BRS_MINI": "1", "BRS_MINI_G": "2", "BRS_NO_CONE": "1"},
+                {"BRS_MINI": "1", "BRS_MINI_G": "8"}, {"BRS_MINI": "1", "BRS_MINI_G": "16", "BRS_NO_RANGE_CULL": "1"},
+                {"BRS_MINI": "1", "BRS_MINI_G": "4", "BRS_SOLO_MAX_CTAS": "1"}):
+        b = _with_env(env, mini)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, env)
+            assert np.array_equal(s[k], b[k]), (k, env, "vs solo range")
+    stats = parity.compare_outputs(scene, b, 6, range(0, B, 4), camera=False)
+    assert stats["max_rel_dist"] < 1e-5 and stats["max_pose_err"] < 1e-9
+
+
+def test_mini_path_fans_config1_flags_noise_and_steps():
+    """Fans of three rays per sensor, an off-centre mount and config 1 on the mini range path;
+    sense-only / move-only steps; seeded noise; brs_steps in one launch."""
+    for scene in (_range_fan_scene(21, 40, 5, 30.0), rb.scenes.config1(n_worlds=50), rb.scenes.config1(n_worlds=3000)):
+        a = _with_env({"BRS_SOLO": "0", "BRS_WIDE": "0", "BRS_GROUP_MIN": "1"}, lambda: parity.run_engine(scene, 5))
+
+        def mini(sc=scene):
+            eng = rb.BatchEngine(sc)
+            assert eng.launch_info()["path"].startswith("mini range"), eng.launch_info()
+            eng.close()
+            return parity.run_engine(sc, 5)
+
+        b = _with_env({"BRS_MINI": "1"}, mini)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        stats = parity.compare_outputs(scene, b, 5, range(0, scene.n_worlds, max(1, scene.n_worlds // 40)), camera=False)
+        assert stats["max_rel_dist"] < 1e-5
+    scene = rb.scenes.config5(n_worlds=700, n_segments=30, n_rays=4)
+
+    def run(env, how):
+        def go():
+            eng = rb.BatchEngine(scene)
+            if how == "noise":
+                eng.set_noise(99, 0.5, 0.0)
+            eng.step()
+            if how == "flags":
+                eng.step(flags=rb.STEP_MOVE)
+                eng.step(flags=rb.STEP_SENSE)
+                eng.step(flags=rb.STEP_MOVE)
+            elif how == "steps":
+                eng.steps(9)
+                assert eng.steps_launches(9) == 1
+            elif how == "single":
+                for _ in range(9):
+                    eng.step()
+            else:
+                eng.step()
+            out = {k: eng.download(k) for k in ("pose", "vel", "stalled", "range")}
+            eng.close()
+            return out
+        return _with_env(env, go)
+
+    fused = {"BRS_SOLO": "0", "BRS_WIDE": "0", "BRS_GROUP_MIN": "1"}
+    for how in ("flags", "noise"):
+        a, b = run(fused, how), run({"BRS_MINI": "1"}, how)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (how, k)
+    a, b = run({"BRS_MINI": "1"}, "single"), run({"BRS_MINI": "1"}, "steps")
+    for k in a:
+        assert np.array_equal(a[k], b[k]), ("steps", k)

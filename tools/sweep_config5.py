@@ -23,7 +23,7 @@ ap.add_argument("--out", default="gpurun_out/sweep_config5.json")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--segments", default="10,30,100,300,1000,2000")
 ap.add_argument("--rays", default="1,4,16,64,256")
-ap.add_argument("--paths", default="auto", help="comma list of auto,fused,solo: launch plans to time per cell")
+ap.add_argument("--paths", default="auto", help="comma list of auto,fused,solo,mini[2|4|8|16]: launch plans to time per cell")
 args = ap.parse_args()
 
 rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -55,10 +55,17 @@ for S in [int(v) for v in args.segments.split(",")]:
         base.robots[0].devices = [rb.RangeSpec(position=(0.0, 0.0), a=360.0 * i / n, max=200.0, width=0.0,
                                                name="ray%d" % i) for i in range(n)]
         for path in args.paths.split(","):
-            if path == "auto":
-                os.environ.pop("BRS_SOLO", None)
-            else:
+            for k in ("BRS_SOLO", "BRS_MINI", "BRS_MINI_G"):
+                os.environ.pop(k, None)
+            if path.startswith("mini"):  # mini, mini2, mini4, mini8, mini16: the team-per-world plan (team size)
+                if n > 16:
+                    continue
+                os.environ["BRS_MINI"] = "1"
+                if path[4:]:
+                    os.environ["BRS_MINI_G"] = path[4:]
+            elif path != "auto":
                 os.environ["BRS_SOLO"] = "1" if path == "solo" else "0"
+                os.environ["BRS_MINI"] = "0"
             eng = rb.BatchEngine(base, device=local_rank)
             tests = eng.count_tests()
             for _ in range(3):
