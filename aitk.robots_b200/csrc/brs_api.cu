@@ -68,6 +68,7 @@ struct brs_engine {
   unsigned long long* d_phase = nullptr;  // BRS_PHASE_TIMING builds
   unsigned long long* d_counters = nullptr;  // [2] executed-work counters (brs_step_counted)
   bool counting = false;
+  bool pdl_chain = false;  // fused kernel launches use programmatic dependent launch (BRS_PDL_CHAIN)
   bool steps_off = false;  // BRS_STEPS_ONE_LAUNCH=0: brs_steps always launches once per step
   int n_group = 0, n_gr = 0, n_dr = 0;
   // launch geometry: threads per CTA, worlds per tile, camera columns per thread, ...
@@ -916,6 +917,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   // ---- brs_step_host pipeline: a copy stream and the events that chain it to the caller's
   e->host_chunks = std::max(1, std::min(8, env_int("BRS_HOST_CHUNKS", cfg->n_worlds >= 8192 ? 4 : 1)));
   e->steps_off = env_int("BRS_STEPS_ONE_LAUNCH", 1) == 0;
+  e->pdl_chain = env_int("BRS_PDL_CHAIN", 1) != 0;
   ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
   for (int k = 0; k < 8 && ce == cudaSuccess; ++k) ce = cudaEventCreateWithFlags(&e->ev_chunk[k], cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming);
@@ -1223,7 +1225,23 @@ static int launch_range(brs_engine* e, int first, int n, double time_step, unsig
   if (e->solo) {
     CK(cudaLaunchKernel(e->s_kfn, dim3(grid), dim3(e->sNT), args, (size_t)e->s_smem, (cudaStream_t)stream));
   } else if (!e->wide && !e->prep_fused) {
-    CK(cudaLaunchKernel(e->kfn, dim3(grid), dim3(e->T), args, (size_t)(msteps ? e->m_smem : e->smem), (cudaStream_t)stream));
+    if (e->pdl_chain) {
+      p.pdl = 1;
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3(grid);
+      lc.blockDim = dim3(e->T);
+      lc.dynamicSmemBytes = (size_t)(msteps ? e->m_smem : e->smem);
+      lc.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      CK(cudaLaunchKernelExC(&lc, e->kfn, args));
+    } else {
+      CK(cudaLaunchKernel(e->kfn, dim3(grid), dim3(e->T), args, (size_t)(msteps ? e->m_smem : e->smem), (cudaStream_t)stream));
+    }
   } else {
     // prep (thread per robot half), then the step kernel under programmatic dependent launch:
     // its prologue and first wall copies overlap the prep kernel, griddepcontrol.wait orders the rest

@@ -208,6 +208,7 @@ struct KParams {
   // assignment, no tile counter -- so step s+1 of a world only ever follows step s of the same
   // world in program order, and the pipelines run on across the step boundaries.
   int n_steps;
+  int pdl;  // fused kernel: launched under programmatic dependent launch (see brs_step_kernel's prologue)
   // fused kernel under brs_steps: [n_tiles][2] epoch words (committed, painted), both equal to
   // epoch0 or less when the launch starts; the host advances epoch0 by n_steps per launch
   unsigned* epoch;
@@ -1752,7 +1753,13 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
 
   const PaintMap pmap = make_paint_map(p, tid, NW);
   // launched behind brs_prep_kernel (programmatic dependent launch): nothing below may pass it
-  if (p.prepped) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // p.pdl: launched with programmatic stream serialization behind whatever precedes it in the
+  // stream (the previous step's kernel, a caller's kernel that wrote the actions): the prologue
+  // above -- barrier init, the camera tables, static data only -- overlaps that kernel's tail and
+  // this grid's own launch latency; everything below waits for its full completion.  The next
+  // launch may be set up as soon as every CTA of this one is past this point.
+  if (p.prepped || p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   BRS_PH_DECL;
   // iteration -1 only lets the helper team step the CTA's first tile
