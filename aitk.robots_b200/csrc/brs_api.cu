@@ -6,6 +6,7 @@
 // entry point that produces results launches brs_step_kernel.
 #include "../../include/brs.h"
 #include "brs_kernels.cuh"
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a tool is attached
 #include "brs_wide.cuh"
 #include "brs_solo.cuh"
 #include "brs_multi.cuh"
@@ -132,6 +133,11 @@ static int pow2ceil(int x) {
   while (p < x) p *= 2;
   return p;
 }
+// NVTX range around a host-side entry point (step / sensors / gather ranges)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -1265,6 +1271,7 @@ static int launch_range(brs_engine* e, int first, int n, double time_step, unsig
 }
 
 extern "C" int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream) {
+  NvtxRange nvtx_("brs_step");
   if (!e) return fail(BRS_ERR_INVALID, "brs_step: null engine");
   if (!(flags & BRS_STEP_ALL)) return BRS_OK;
   CK(cudaSetDevice(e->cfg.device));
@@ -1305,6 +1312,7 @@ extern "C" int brs_steps_info(brs_engine* e, int* worlds_per_tile, int* n_tiles,
   return BRS_OK;
 }
 extern "C" int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_steps, void* stream) {
+  NvtxRange nvtx_("brs_steps");
   if (!e) return fail(BRS_ERR_INVALID, "brs_steps: null engine");
   if (n_steps < 0) return fail(BRS_ERR_INVALID, "brs_steps: n_steps < 0");
   if (!(flags & BRS_STEP_ALL) || n_steps == 0) return BRS_OK;
@@ -1356,6 +1364,7 @@ extern "C" int brs_set_noise(brs_engine* e, unsigned long long seed, unsigned fi
 
 extern "C" int brs_step_counted(brs_engine* e, double time_step, unsigned flags, void* stream,
                                 unsigned long long* ray_tests, unsigned long long* edge_tests) {
+  NvtxRange nvtx_("brs_step_counted");
   if (!e) return fail(BRS_ERR_INVALID, "brs_step_counted: null engine");
   CK(cudaSetDevice(e->cfg.device));
   if (!e->d_counters) CK(cudaMalloc((void**)&e->d_counters, 16));
@@ -1379,6 +1388,7 @@ extern "C" int brs_step_counted(brs_engine* e, double time_step, unsigned flags,
 extern "C" int brs_step_host(brs_engine* e, double time_step, unsigned flags, const double* h_target_vel,
                              double* h_pose, uint8_t* h_stalled, float* h_range, uint8_t* h_camera, float* h_light,
                              float* h_smell, void* stream) {
+  NvtxRange nvtx_("brs_step_host");
   if (!e) return fail(BRS_ERR_INVALID, "brs_step_host: null engine");
   CK(cudaSetDevice(e->cfg.device));
   const int B = e->cfg.n_worlds, C = std::max(1, std::min(e->host_chunks, B));
@@ -1467,6 +1477,7 @@ extern "C" int brs_host_free(brs_engine* e, void* host) {
 // Top-down pictures of worlds [first, first + n): see brs_render_kernel (brs_kernels.cuh).
 extern "C" int brs_render_world(brs_engine* e, int first_world, int n_worlds, int img_w, int img_h, int robot,
                                 double view_w, double view_h, double line_px, double bulb_px, void* d_out, void* stream) {
+  NvtxRange nvtx_("brs_render_world");
   if (!e || !d_out) return fail(BRS_ERR_INVALID, "brs_render_world: null argument");
   const brs_config& c = e->cfg;
   if (first_world < 0 || n_worlds < 1 || first_world + n_worlds > c.n_worlds || img_w < 1 || img_h < 1 || img_w > 8192 || img_h > 8192)

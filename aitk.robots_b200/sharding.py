@@ -109,7 +109,19 @@ class ShardedWorlds:
         return full
 
     def all_gather(self, name):
-        """Observation `name` of every world on every rank."""
+        """Observation `name` of every world on every rank (NVTX range "brs_gather:<name>")."""
+        import torch
+
+        nvtx = torch.cuda.nvtx if torch.cuda.is_available() else None
+        if nvtx is not None:
+            nvtx.range_push("brs_gather:%s" % name)
+        try:
+            return self._all_gather(name)
+        finally:
+            if nvtx is not None:
+                nvtx.range_pop()
+
+    def _all_gather(self, name):
         if name in self._fused:
             # the step kernels already stored every rank's pictures everywhere: wait for all of them
             _dist().all_reduce(self._token, group=self.group)
