@@ -656,6 +656,15 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   mnb = std::min(mnb, env_int("BRS_MAX_CTAS_PER_SM", 32));
   e->m_grid = std::max(1, std::min(e->m_tiles, mnb * e->sm_count));
   e->m_fused_table = env_int("BRS_FUSED_TABLE", e->mTW * e->n_group >= e->NW / 32 ? 1 : 0);
+  {
+    // per-tile epoch words of brs_steps (committed, painted): all zero = epoch0
+    cudaError_t ee = cudaMalloc((void**)&e->d_epoch, (size_t)std::max(e->m_tiles, 1) * 8);
+    if (ee == cudaSuccess) ee = cudaMemset(e->d_epoch, 0, (size_t)std::max(e->m_tiles, 1) * 8);
+    if (ee != cudaSuccess) {
+      brs_destroy(e);
+      return fail(BRS_ERR_CUDA, std::string("brs_create: epoch words: ") + cudaGetErrorString(ee));
+    }
+  }
 
   // ---- the wide path: launch geometry ------------------------------------------
   // One team (CTA) per tile, no helper warps.  A one-warp team wherever a tile of worlds fits
@@ -1319,16 +1328,9 @@ extern "C" int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_
   CK(cudaSetDevice(e->cfg.device));
   const bool one_launch = steps_one_launch(e, flags, n_steps);
   if (one_launch) {
-    const int tiles = e->solo ? 1 : std::max(e->m_tiles, 1);
     const int piece = steps_piece(e, n_steps);
     for (int done = 0; done < n_steps;) {
       const int n = std::min(piece, n_steps - done);
-      if (!e->solo && !e->d_epoch) {
-        CK(cudaMalloc((void**)&e->d_epoch, (size_t)tiles * 8));
-        CK(cudaMemsetAsync(e->d_epoch, 0, (size_t)tiles * 8, (cudaStream_t)stream));
-        e->epoch0 = 0;
-        e->kp_flags = 0xffffffffu;  // the cached parameters carry the pointer
-      }
       const int rc = launch_range(e, 0, e->cfg.n_worlds, time_step, flags, stream, n);
       if (rc) return rc;
       if (!e->solo && n > 1) e->epoch0 += (unsigned)n;
