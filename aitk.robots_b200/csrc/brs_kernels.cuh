@@ -1785,35 +1785,35 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
           // order than what it waits for, and every CTA of the grid is resident: no deadlock.
           // (a batch of no more tiles than CTAs: CTA b keeps tile b for every step -- program
           // order does the rest, no counter, no epochs; config 1 as written is this case)
-          const bool own = p.n_tiles <= (int)gridDim.x;
           unsigned* const ep = p.epoch;
-          if (own) {
+          if (p.n_tiles <= (int)gridDim.x) {
             tn = ((int)blockIdx.x < p.n_tiles && it + 1 < p.n_steps) ? (int)blockIdx.x : p.n_tiles;
             sched[3 + (buf ^ 1)] = 1;
           } else {
-          if (h_prev1 >= 0) st_release_gpu(ep + 2 * (h_prev1 % p.n_tiles), p.epoch0 + (unsigned)(h_prev1 / p.n_tiles) + 1u);
-          if (h_prev2 >= 0) st_release_gpu(ep + 2 * (h_prev2 % p.n_tiles) + 1, p.epoch0 + (unsigned)(h_prev2 / p.n_tiles) + 1u);
-          // (every item comes from the counter, the first one too: a CTA that is not resident yet owns nothing)
-          const long long k = (long long)atomicAdd(&p.sched[0], 1u);
-          int ok = 1;
-          unsigned want = 0;
-          if (k < (long long)p.n_steps * p.n_tiles) {
-            tn = (int)(k % p.n_tiles);
-            const unsigned sk = (unsigned)(k / p.n_tiles);
-            if (sk > 0) {
-              want = p.epoch0 + sk;
-              while ((int)(ld_relaxed_gpu(ep + 2 * tn) - want) < 0) __nanosleep(64);
-              ok = (int)(ld_relaxed_gpu(ep + 2 * tn + 1) - want) >= 0;
+            if (h_prev1 >= 0)
+              st_release_gpu(ep + 2 * (h_prev1 % p.n_tiles), p.epoch0 + (unsigned)(h_prev1 / p.n_tiles) + 1u);
+            if (h_prev2 >= 0)
+              st_release_gpu(ep + 2 * (h_prev2 % p.n_tiles) + 1, p.epoch0 + (unsigned)(h_prev2 / p.n_tiles) + 1u);
+            // (every item comes from the counter, the first one too: a CTA that is not resident yet owns nothing)
+            const long long k = (long long)atomicAdd(&p.sched[0], 1u);
+            int ok = 1;
+            unsigned want = 0;
+            h_prev2 = h_prev1;
+            if (k < (long long)p.n_steps * p.n_tiles) {
+              tn = (int)(k % p.n_tiles);
+              const unsigned sk = (unsigned)(k / p.n_tiles);
+              if (sk > 0) {
+                want = p.epoch0 + sk;
+                while ((int)(ld_relaxed_gpu(ep + 2 * tn) - want) < 0) __nanosleep(64);
+                ok = (int)(ld_relaxed_gpu(ep + 2 * tn + 1) - want) >= 0;
+              }
+              h_prev1 = (int)k;
+            } else {
+              tn = p.n_tiles;
+              h_prev1 = -1;
             }
-            h_prev2 = h_prev1;
-            h_prev1 = (int)k;
-          } else {
-            tn = p.n_tiles;
-            h_prev2 = h_prev1;
-            h_prev1 = -1;
-          }
-          sched[3 + (buf ^ 1)] = ok;
-          sched[5 + (buf ^ 1)] = (int)want;
+            sched[3 + (buf ^ 1)] = ok;
+            sched[5 + (buf ^ 1)] = (int)want;
           }
         } else {
           tn = it < 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(&p.sched[0], 1u));
