@@ -517,10 +517,40 @@ def e2e_measure(bench, eng, scene, steps):
     c1.record(bench.stream)
     bench.barrier()
     copy_ms = c0.elapsed_time(c1)
-    e2e_ms, copy_ms = bench.reduce([e2e_ms, copy_ms])
+    # context: the same loop for a consumer that lives on the GPU (an RL policy reading the zero-copy
+    # picture tensor): actions host->device, poses / stall flags / range readings device->host, the
+    # pictures painted every step but left in HBM
+    small_ms, small_d2h = None, 0
+    if eng.n_camera:
+        def small_step():
+            eng.step_host(flags=flags, target_vel=h_tvel.data_ptr(), pose=h_pose.data_ptr(), stalled=h_stalled.data_ptr(),
+                          range_=h_range.data_ptr() if eng.n_range else 0, camera=0,
+                          light=h_light.data_ptr() if eng.n_light else 0, smell=h_smell.data_ptr() if eng.n_smell else 0,
+                          stream=bench.sh)
+
+        for _ in range(3):
+            small_step()
+        bench.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(bench.stream)
+        for _ in range(n):
+            small_step()
+        s1.record(bench.stream)
+        bench.barrier()
+        bench.launches += n * eng.launch_info()["launches_per_step"]
+        small_ms = s0.elapsed_time(s1)
+        small_d2h = d2h - eng.n_camera * B * eng.cam_h * eng.cam_w * 4
+    e2e_ms, copy_ms, small_ms = bench.reduce([e2e_ms, copy_ms, small_ms if small_ms is not None else 0.0])
     ws = bench.world_size
     nbytes = big.numel() * big.element_size()
-    return {"value": ws * B * n / (e2e_ms * 1e-3), "unit": "world-steps/s", "h2d_bytes_per_step": int(h2d) * ws,
+    extra = {}
+    if eng.n_camera:
+        extra["pictures_left_on_device"] = {
+            "value": ws * B * n / (small_ms * 1e-3), "unit": "world-steps/s", "ms_per_step": small_ms / n,
+            "h2d_bytes_per_step": int(h2d) * ws, "d2h_bytes_per_step": int(small_d2h) * ws,
+            "note": "same brs_step_host loop, every picture painted each step but read by a consumer on the GPU "
+                    "(zero-copy tensor) instead of being shipped to the host: what the PCIe drain costs"}
+    return {**extra, "value": ws * B * n / (e2e_ms * 1e-3), "unit": "world-steps/s", "h2d_bytes_per_step": int(h2d) * ws,
             "d2h_bytes_per_step": int(d2h) * ws, "ms_per_step": e2e_ms / n,
             "api": "brs_step_host (C ABI, pinned host buffers; kernel of chunk c+1 overlaps the copies of chunk c)",
             "achieved_d2h_gbs": d2h * ws * n / (e2e_ms * 1e-3) / 1e9,
