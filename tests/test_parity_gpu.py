@@ -1092,3 +1092,49 @@ def test_mini_path_fans_config1_flags_noise_and_steps():
     a, b = run({"BRS_MINI": "1"}, "single"), run({"BRS_MINI": "1"}, "steps")
     for k in a:
         assert np.array_equal(a[k], b[k]), ("steps", k)
+
+
+def test_steps_epoch_protocol_soak():
+    """Stress of brs_steps on the fused kernel where the epoch words matter: batches of a few
+    more tiles than CTAs (so that consecutive steps of a tile keep landing on other CTAs, some
+    of them while the previous step's observations are still being written), random step
+    counts and tile sizes, 40 cases each run four times -- always bit-identical to single steps."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    makers = [
+        lambda n, s: rb.scenes.demo_scene(n, seed=s),
+        lambda n, s: rb.scenes.config2(n_worlds=n, seed=s, cam_w=32, cam_h=16),
+        lambda n, s: rb.scenes.config3(n_worlds=n, seed=s),
+        lambda n, s: rb.scenes.config5(n_worlds=n, n_segments=40, n_rays=6, seed=s),
+        lambda n, s: rb.scenes.config4(n_worlds=n, seed=s, cam_w=32, cam_h=16),
+    ]
+    cases = 0
+    for it in range(40):
+        mk = makers[it % len(makers)]
+        tw = int(rng.choice([1, 1, 2, 3]))
+        n = int(rng.integers(600, 1400)) * tw
+        k = int(rng.integers(5, 40))
+        scene = mk(n, int(rng.integers(1, 10 ** 6)))
+        env = {"BRS_SOLO": "0", "BRS_WIDE": "0", "BRS_STEPS_TW": str(tw)}
+
+        def run(how):
+            eng = rb.BatchEngine(scene)
+            assert eng.launch_info()["path"].startswith("fused ("), eng.launch_info()
+            if how == "single":
+                for _ in range(k):
+                    eng.step()
+            else:
+                assert eng.steps_launches(k) == 1 and eng.steps_info()["tiles"] > eng.steps_info()["ctas"]
+                eng.steps(k)
+            out = {b: eng.download(b) for b in ("pose", "vel", "stalled", "range", "light", "smell")}
+            if eng.n_camera:
+                out["camera"] = eng.download("camera")
+            eng.close()
+            return out
+
+        a = _with_env(env, lambda: run("single"))
+        for rep in range(4):
+            b = _with_env(env, lambda: run("steps"))
+            for key in a:
+                assert np.array_equal(a[key], b[key]), (it, rep, key, n, k, tw)
+        cases += 1
+    assert cases == 40
