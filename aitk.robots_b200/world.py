@@ -186,6 +186,7 @@ class Robot:
         self.name = name
         self._slot = None
         self._pose = [float(x), float(y), float(a) * PI_OVER_180]
+        self._pose0 = list(self._pose)  # what World.reset() returns to
         self._tvel = [0.0, 0.0, 0.0]
         self.color = to_rgba(color)
         self.height = float(height)
@@ -235,6 +236,8 @@ class Robot:
             cur[2] = float(a) * PI_OVER_180
         self._pose = cur
         self._pending = True
+        if self.world is None or self.world._engine is None:
+            self._pose0 = list(cur)  # placed before the first step: that is the initial pose
         if self.world is not None:
             # a pose change is an upload of one row into the live engine, not a rebuild:
             # velocities, stall flags and every other robot keep their state
@@ -582,3 +585,42 @@ class World:
     def seconds(self, seconds, time_step=None):
         dt = self.time_step if time_step is None else time_step
         self.steps(round(seconds / dt), time_step)
+
+    def run(self, function=None, time_step=None, max_steps=None):
+        """Step until ``function(world)`` returns a true value (upstream World.run: the
+        controller loop [RECALL]; the real-time / display options of upstream have no meaning
+        here).  The controller is called before every step; without one, runs ``max_steps``."""
+        n = 0
+        while max_steps is None or n < max_steps:
+            if function is not None and function(self):
+                break
+            if function is None and max_steps is None:
+                raise ValueError("World.run needs a controller function or max_steps")
+            self.step(time_step)
+            n += 1
+        return n
+
+    def reset(self):
+        """Back to the state the world was built with: robots at their constructor poses (or
+        the last set_pose before the first step), zero velocities, clock at 0 (upstream
+        World.reset [RECALL])."""
+        for r in self._robots:
+            r._pose = list(r._pose0)
+            r._tvel = [0.0, 0.0, 0.0]
+            r._pending = True
+        self.time = 0.0
+        self._sensed = False
+        if self._engine is not None:
+            self._engine.upload("pose", np.array([[r._pose for r in self._robots]], dtype=np.float64))
+            zeros = np.zeros((1, len(self._robots), 3), dtype=np.float64)
+            self._engine.upload("vel", zeros)
+            self._engine.upload("target_vel", zeros)
+            self._engine.upload("stalled", np.zeros((1, len(self._robots)), dtype=np.uint8))
+            for r in self._robots:
+                r._pending = False
+            self._pose_dirty = False
+            self._pull_state()
+
+    def get_robot(self, item):
+        """Robot by index or name (upstream: ``world[item]``)."""
+        return self[item]

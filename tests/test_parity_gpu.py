@@ -1138,3 +1138,24 @@ def test_steps_epoch_protocol_soak():
                 assert np.array_equal(a[key], b[key]), (it, rep, key, n, k, tw)
         cases += 1
     assert cases == 40
+
+
+def test_facade_run_and_reset():
+    w = rb.World(200, 150)
+    r = rb.Robot(50, 75, 0)
+    r.add_device(rb.RangeSensor(position=(8, 0), a=0, max=100, width=0))
+    w.add_robot(r)
+    r.move(1.0, 0.0)
+    first = None
+
+    def controller(world):
+        return world[0][0].get_distance() < 30.0  # stop 30 units from the wall ahead
+
+    n = w.run(controller)
+    assert n > 10 and r[0].get_distance() < 30.0 and r.x > 100 and w.time == round(n * 0.1, 10)
+    first = (r.x, r.y, r.a, n)
+    w.reset()
+    assert (r.x, r.y, r.a) == (50.0, 75.0, 0.0) and w.time == 0.0 and not r.stalled
+    r.move(1.0, 0.0)
+    assert w.run(controller) == n and (r.x, r.y, r.a, n) == first  # the same run again, bit for bit
+    assert w.run(max_steps=5) == 5 and w.get_robot(0) is r
