@@ -102,6 +102,7 @@ struct brs_engine {
   bool mini = false;
   int mini_G = 4, mini_NRAY = 1;
   // the solo multi path (brs_multi_kernel): several robots (or several mounts), no camera
+  bool use_rmask = true;   // fused / wide: warp-built reach masks for the direct-path range sensors (BRS_RMASK)
   bool use_rlist = false;  // fused / wide: per-robot lists of reachable segments for the direct-path range sensors
   bool multi = false;
   MultiRay* d_multi_rays = nullptr;
@@ -932,6 +933,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   // ---- brs_step_host pipeline: a copy stream and the events that chain it to the caller's
   e->host_chunks = std::max(1, std::min(8, env_int("BRS_HOST_CHUNKS", cfg->n_worlds >= 8192 ? 4 : 1)));
   e->steps_off = env_int("BRS_STEPS_ONE_LAUNCH", 1) == 0;
+  e->use_rmask = env_int("BRS_RMASK", 1) != 0;
   e->pdl_chain = env_int("BRS_PDL_CHAIN", 1) != 0;
   ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
   for (int k = 0; k < 8 && ce == cudaSuccess; ++k) ce = cudaEventCreateWithFlags(&e->ev_chunk[k], cudaEventDisableTiming);
@@ -1193,6 +1195,14 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
   for (int r = 0; r < 8; ++r) p.m_reach[r] = e->multi_reach[r];
   if (e->multi) {
     p.m_rays = e->d_multi_rays; p.m_nrays = e->multi_nrays; p.m_bw = e->multi_bw;
+  }
+  {
+    // reach masks for the direct-path range sensors: one lane per ray, every segment of a world
+    // in one ballot, and enough sensors per robot that a warp spans only a few robots
+    const int sld = wide ? e->wSLD : (msteps ? e->mSLD : e->SLD);
+    const int team = wide ? e->wNT : (e->direct_on_helper ? 32 * e->NH : e->NW);
+    p.use_rmask = (e->use_rmask && !e->solo && !e->use_rlist && sld == 1 && team % 32 == 0 &&
+                   c.seg_cap + 4 * c.n_robots <= 32 && e->n_dr >= 8 * c.n_robots) ? 1 : 0;
   }
   if (e->use_rlist && !e->solo) {
     const int tw = wide ? e->wTW : (msteps ? e->mTW : e->TW), R = c.n_robots, nvis = c.seg_cap + 4 * R;

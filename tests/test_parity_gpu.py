@@ -238,6 +238,7 @@ def test_culling_and_tiling_never_change_results(maker):
                 {"BRS_WIDE": "0", "BRS_TW": "5", "BRS_BIG": "1"},
                 {"BRS_WIDE": "0", "BRS_NH": "2"}, {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "1"},
                 {"BRS_WIDE": "0", "BRS_RLIST": "1"}, {"BRS_WIDE": "1", "BRS_RLIST": "1", "BRS_WNT": "64"},
+                {"BRS_WIDE": "0", "BRS_RMASK": "0"}, {"BRS_WIDE": "0", "BRS_RMASK": "0", "BRS_TW": "3"},
                 {"BRS_WIDE": "0", "BRS_DIRECT_ON_HELPER": "0", "BRS_TW": "2"},
                 {"BRS_WIDE": "0", "BRS_NR": "1", "BRS_GROUP_MIN": "1000"},
                 {"BRS_WIDE": "0", "BRS_PREP": "1"}, {"BRS_WIDE": "0", "BRS_PREP": "1", "BRS_TW": "3", "BRS_BIG": "1"},
