@@ -571,6 +571,12 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     e->direct_on_helper = env_int("BRS_DIRECT_ON_HELPER", e->direct_on_helper ? 1 : 0) != 0 && dtasks > 0;
     int nh = (int)std::lround(T_total / 32.0 * helper_w / (helper_w + worker_w));
     nh = std::max(1, std::min(nh, T_total / 32 - 1));
+    // multi-robot worlds whose range searches run over reach masks (sense_direct): the masks
+    // halve the workers' share, and one helper warp stepping R robots per world (pair
+    // collisions, list-order replay) then gates them -- measured on config 3: 0.196 -> 0.185 ms
+    // per step, 0.200 -> 0.172 under brs_steps, with two
+    if (R >= 2 && env_int("BRS_RMASK", 1) != 0 && !e->n_gr && cfg->seg_cap + 4 * R <= 32 && e->n_dr >= 8 * R && !e->big)
+      nh = std::max(nh, 2);
     nh = env_int("BRS_NH", nh);
     nh = std::max(1, std::min(nh, T_total / 32 - 1));
     e->NH = nh;
