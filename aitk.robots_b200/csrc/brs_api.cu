@@ -79,6 +79,7 @@ struct brs_engine {
   int mTW = 1, mSLG = 1, mSLD = 1, mSLL = 1, m_paint_rs = 1, m_tiles = 1, m_grid = 1, m_smem = 0, m_fused_table = 0;
   int gtasks = 0, dtasks = 0;
   bool big = false, direct_on_helper = false;
+  bool split_lights = false;  // helper team: light + smell sensors, workers: range sensors (KParams::direct_on_helper == 2)
   int fused_table = 0;
   const void* kfn = nullptr;
   // the wide path (brs_wide.cuh): prep kernel + one-team-per-tile step kernel
@@ -577,6 +578,10 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
     // per step, 0.200 -> 0.172 under brs_steps, with two
     if (R >= 2 && env_int("BRS_RMASK", 1) != 0 && !e->n_gr && cfg->seg_cap + 4 * R <= 32 && e->n_dr >= 8 * R && !e->big)
       nh = std::max(nh, 2);
+    // ... and those helper warps still wait for the workers most of the time: they take the
+    // light and smell sensors of the tile they just committed
+    e->split_lights = R >= 2 && nh >= 2 && !e->direct_on_helper && (cfg->n_light + cfg->n_smell) > 0 && e->n_dr > 0 &&
+                      env_int("BRS_SPLIT_LIGHTS", 1) != 0;
     nh = env_int("BRS_NH", nh);
     nh = std::max(1, std::min(nh, T_total / 32 - 1));
     e->NH = nh;
@@ -629,7 +634,7 @@ extern "C" int brs_create(const brs_config* cfg, brs_engine** out) {
   auto lanes_for = [&](int t, int& slg, int& sld, int& sll, int& prs) {
     slg = gtasks ? std::min(32, pow2floor(std::max(e->NW / (gtasks * t), 1))) : 1;
     sld = e->n_dr ? std::min(32, pow2floor(std::max(dteam / (e->n_dr * t), 1))) : 1;
-    sll = cfg->n_light ? std::min(32, pow2floor(std::max(dteam / (cfg->n_light * t), 1))) : 1;
+    sll = cfg->n_light ? std::min(32, pow2floor(std::max((e->split_lights ? 32 * e->NH : dteam) / (cfg->n_light * t), 1))) : 1;
     const int Q = std::max(e->cam_w / 4, 1);
     const int slots = std::max(e->NW / std::min(Q, e->NW), 1);
     const int nislot = std::max(1, std::min(t * std::max(cfg->n_camera, 1), slots));
@@ -1148,7 +1153,7 @@ static void fill_params_uncached(brs_engine* e, KParams& p, double time_step, un
     p.cq_max = wide_cq_max(e->wTW, c.n_robots);
   } else {
     p.TW = e->TW; p.n_tiles = e->n_tiles; p.SLG = e->SLG; p.SLD = e->SLD; p.SLL = e->SLL; p.paint_rs = e->paint_rs;
-    p.direct_on_helper = e->direct_on_helper ? 1 : 0;
+    p.direct_on_helper = e->direct_on_helper ? 1 : (e->split_lights ? 2 : 0);
     p.fused_table = e->fused_table;
     if (msteps) {
       p.TW = e->mTW; p.n_tiles = e->m_tiles; p.SLG = e->mSLG; p.SLD = e->mSLD; p.SLL = e->mSLL; p.paint_rs = e->m_paint_rs;

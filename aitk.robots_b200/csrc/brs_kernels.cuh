@@ -138,7 +138,7 @@ struct KParams {
   int SLG, SLD, SLL; // lanes per ray task: group path, direct range path, light path (powers of two <= 32)
   int n_gr, n_dr;    // range sensors on the group path / on the direct path
   int paint_rs;      // row slots of the paint phase
-  int direct_on_helper;  // the helper team runs the direct-path sensors (camera worlds with few of them)
+  int direct_on_helper;  // 1: the helper team runs the direct-path sensors (camera worlds with few of them); 2: only the light and smell sensors (the workers keep the ranges)
   int fused_table;   // TABLE phase: one warp per (world, group) builds and compacts in one pass
   int flat_rows;     // sky and ground rows are one colour each (no vertical gradient)
   int NW;            // worker threads (ray tasks); the CTA has NW + 32*NH threads
@@ -1013,14 +1013,16 @@ __device__ __forceinline__ void prepare_tile(const KParams& p, int w0, int nw, i
 // device kind: mixing kinds in a warp would serialise their code paths.  Either team can
 // run this: the workers for sensor-heavy worlds, the otherwise idle helper team for
 // camera worlds with a few extra sensors (right after it committed the tile's poses).
+// `kinds`: which device kinds this call runs (1 range, 2 light, 4 smell) -- worlds whose helper
+// team has time to spare hand it the light and smell sensors while the workers keep the ranges.
 __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, int bid, int lane, int w0, int nw,
                                              const uint32_t* __restrict__ rawb, const float4* __restrict__ segtab,
-                                             const double* __restrict__ wsb, const int2* __restrict__ meta) {
+                                             const double* __restrict__ wsb, const int2* __restrict__ meta, int kinds) {
   const int R = p.n_robots, SC = p.seg_cap, nvis = SC + 4 * R;
   extern __shared__ __align__(128) unsigned char brs_dyn_smem[];
   uint8_t* const rlist = (uint8_t*)(brs_dyn_smem + p.rl_off);
   int* const rcnt = (int*)(brs_dyn_smem + p.rc_off);
-  const bool use_rlist = p.use_rlist && p.n_dr > 0;
+  const bool use_rlist = p.use_rlist && p.n_dr > 0 && (kinds & 1);
   if (use_rlist) {
     // Which segments can a robot's range rays reach at all?  One warp per (world, robot): FP32
     // distance of the final centre to every segment (walls and the other robots' box edges)
@@ -1063,7 +1065,7 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
   // predicate of the lists above -- and the ballot IS the robot's list: a 32-bit mask the rays
   // then walk in index order.  No shared memory, no barrier beyond the warp.  In a 300 x 300
   // room with 60-unit sensors two tests in three drop out; the rest is evaluated exactly as below.
-  if (p.n_dr > 0 && p.use_rmask) {
+  if ((kinds & 1) && p.n_dr > 0 && p.use_rmask) {
     const int ntask = p.n_dr, total = nw * ntask;
     for (int ib = tt & ~31; ib < total; ib += tn) {
       const int i = ib + lane;
@@ -1127,9 +1129,8 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
       p.range_out[(size_t)w * p.n_range + si] = range_reading(p, w, si, (float)best, (float)sd.max);
       if (p.counters) atomicAdd(&p.counters[0], (unsigned long long)sd.n_rays * __popc(mymask));
     }
-  } else
-  // range sensors on their own mount ...
-  if (p.n_dr > 0) {
+  } else if ((kinds & 1) && p.n_dr > 0) {
+    // range sensors on their own mount ...
     const int SL = p.SLD, g = tt & (SL - 1), slot = tt / SL, nslot = tn / SL;
     const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
     const int ntask = p.n_dr;
@@ -1188,7 +1189,7 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
     }
   }
   // ... light sensors: line of sight to every bulb ...
-  if (p.n_light > 0) {
+  if ((kinds & 2) && p.n_light > 0) {
     const int SL = p.SLL, g = tt & (SL - 1), slot = tt / SL, nslot = tn / SL;
     const uint32_t gmask = (SL == 32) ? 0xffffffffu : (((1u << SL) - 1u) << (lane & ~(SL - 1)));
     const int ntask = p.n_light;
@@ -1229,7 +1230,7 @@ __device__ __forceinline__ void sense_direct(const KParams& p, int tt, int tn, i
     }
   }
   // ... smell sensors: grid lookup at the mount point
-  if (p.n_smell > 0) {
+  if ((kinds & 4) && p.n_smell > 0) {
     const int ntask = p.n_smell;
     for (int i = tt; i < nw * ntask; i += tn) {
       const int wl = (int)fdiv(i, p.dST), si = i - wl * ntask, w = w0 + wl;
@@ -1524,7 +1525,7 @@ __device__ BRS_INL_ROBOT void collide_commit_tile(const KParams& p, int w0, int 
   // do not -- run the direct-path sensors of this tile here, on the poses just committed
   if (do_direct) {
     team_sync(bid, nth);
-    sense_direct(p, ht, nth, bid, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta);
+    sense_direct(p, ht, nth, bid, threadIdx.x & 31, w0, nw, rawb, segtab, wsb, meta, p.direct_on_helper == 2 ? 6 : 7);
   }
   BRS_PH(ht == 0, 13);
 }
@@ -1758,7 +1759,7 @@ __device__ __forceinline__ void sense_paint_tile(const KParams& p, const int tid
         }
       }
       // 5b. direct path (unless the helper team already ran it for this tile)
-      if (do_sense && direct_here) sense_direct(p, tid, NW, 1, lane, w0, nw, rawb, segtab, wsb, meta);
+      if (do_sense && direct_here) sense_direct(p, tid, NW, 1, lane, w0, nw, rawb, segtab, wsb, meta, p.direct_on_helper == 2 ? 1 : 7);
 
       BRS_PH(tid == 0, 2);
       // ---------------- PAINT ----------------------------------------------------------------
@@ -1937,7 +1938,7 @@ __global__ void __launch_bounds__(BIG ? BRS_BIG_THREADS : BRS_SMALL_THREADS, BIG
       }
       BRS_PH(tid == 0, 0);
 
-      sense_paint_tile<NR>(p, tid, NW, lane, w0, nw, do_sense, do_cam, !p.direct_on_helper, rawb, segtab, wsb, meta, org,
+      sense_paint_tile<NR>(p, tid, NW, lane, w0, nw, do_sense, do_cam, p.direct_on_helper != 1, rawb, segtab, wsb, meta, org,
                            gcull, gtab, gidx, gcnt, colinfo, strips, camcs, rowsky, rowgnd, pmap);
     }
     BRS_PH(tid == NW, 14);
