@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call r3g: evidence for the final kernels -- tests, bench lines, launch lists, full captures
 set -u
-OUT=gpurun_out/r3g; mkdir -p $OUT
+OUT=gpurun_out/${TAG:-r3g}; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
 timeout 700 python -m pytest tests -m gpu -x -q --durations=5 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_gpu.log
 timeout 600 python bench.py > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench rc=$?"
