@@ -319,7 +319,9 @@ __host__ __device__ inline SmemLayout make_layout(int TW, int seg_cap, int R, in
 // optimum for worlds that fit several CTAs per SM), or 256 + 32 at 2 CTAs/SM for worlds
 // whose shared-memory footprint leaves room for one or two CTAs only
 #define BRS_SMALL_THREADS 160
+#ifndef BRS_SMALL_CTAS
 #define BRS_SMALL_CTAS 4
+#endif
 #define BRS_BIG_THREADS 288
 #define BRS_BIG_CTAS 2
 // one-warp teams of the wide path: resident CTAs per SM the register cap is set for
