@@ -168,11 +168,11 @@ int brs_step(brs_engine* e, double time_step, unsigned flags, void* stream);
  * now (upstream world.py: World.steps(steps) / World.seconds(seconds) -- the loop config 1 of
  * BASELINE.json is written as: 1000 steps of one world).  Same results, bit for bit, as n
  * calls of brs_step; every step writes all of its observations, the buffers end up holding the
- * last step's.  ONE launch when the active plan supports it (the fused, solo and solo range
- * kernels: a tile / world then stays with one CTA / warp for the whole launch, so its steps
- * follow each other in program order and the kernel's pipeline runs on across the step
- * boundaries instead of filling and draining once per step); n launches when sensor noise is
- * on, with BRS_STEPS_ONE_LAUNCH=0, or on the opt-in plans. */
+ * last step's.  ONE launch when the active plan supports it (the fused, solo, solo range and
+ * mini range kernels: a world stays with one warp / team for the whole launch -- on the fused
+ * kernel a tile's steps are ordered across CTAs by per-tile epoch words -- so the kernel's
+ * pipeline runs on across the step boundaries instead of filling and draining once per step);
+ * n launches when sensor noise is on, with BRS_STEPS_ONE_LAUNCH=0, or on the opt-in plans. */
 int brs_steps(brs_engine* e, double time_step, unsigned flags, int n_steps, void* stream);
 /* How many kernel launches brs_steps(flags, n_steps) issues on this engine as configured now. */
 int brs_steps_launches(brs_engine* e, unsigned flags, int n_steps, int* launches);
