@@ -39,13 +39,16 @@ def make_scene(rb, config, n_worlds, first_world):
         return g.config3(n_worlds=n_worlds, first_world=first_world)
     if config == "config4":
         return g.config4(n_worlds=n_worlds, first_world=first_world)
+    if config == "config4-random":  # the random-segment variant of the 100-segment worlds
+        return g.config4(n_worlds=n_worlds, first_world=first_world, variant="random")
     if config.startswith("config5"):
         _, S, R = config.split("-")  # config5-<segments>-<rays>
         return g.config5(n_worlds=n_worlds, n_segments=int(S), n_rays=int(R), first_world=first_world)
     raise SystemExit("unknown config %r" % config)
 
 
-DEFAULT_WORLDS = {"config1": 4096, "config2": 4096, "config2-boxes": 4096, "config3": 65536, "config4": 131072}
+DEFAULT_WORLDS = {"config1": 4096, "config2": 4096, "config2-boxes": 4096, "config3": 65536, "config4": 131072,
+                  "config4-random": 131072}
 
 
 def describe(config, scene):
@@ -866,6 +869,8 @@ def main():
             ex["config2_boxes"] = summarize(w)  # the "20 boxes = 80 segments" reading of configs[1]
             w, _, _ = bench.workload("config3", DEFAULT_WORLDS["config3"], steps_x, 3)
             ex["config3"] = summarize(w)
+            w, _, _ = bench.workload("config4-random", DEFAULT_WORLDS["config4-random"], steps_x, 3)
+            ex["config4_random_segments"] = summarize(w)  # config 4 with 100 random segments instead of a grid maze
         # config 4: 1,048,576 worlds split over the ranks (N = 1: one eighth, the 8-GPU shard)
         per_rank = (1 << 20) // max(world_size, 8 if world_size == 1 else world_size)
         w, e4, s4 = bench.workload("config4", per_rank, steps_x, 3, keep=True)
